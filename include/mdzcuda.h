@@ -1,0 +1,150 @@
+/*
+ * mdzcuda.h -- C ABI of libmdzcuda, the B200 replacement for MDZ's per-pixel
+ * escape-time path.
+ *
+ * Two layers are exported from the same shared library:
+ *
+ *  1. The reference's own render-pool API, unchanged: the fourteen rth_*
+ *     functions and the rthdata struct of reference src/render_threads.h:20-87.
+ *     Those are declared in include/mdz_rth.h.  Linking MDZ against libmdzcuda
+ *     instead of compiling src/render_threads.c is the whole integration
+ *     (INTEGRATION.md).
+ *
+ *  2. The plain entry points below, which the rth_* layer is built on and which
+ *     a host without MDZ's image_info (tests, bench.py, another language's FFI)
+ *     can bind directly.  Only C scalars, plain pointers and the public
+ *     mpfr_t / mpf_t structs cross this boundary.
+ *
+ * A render is described by an mdzcuda_view: exactly the fields that the
+ * reference's three line drivers read from image_info at render time
+ * (src/fractal.c:29-117, :120-257, :260-397; field list in
+ * src/image_info.h:63-122).
+ */
+#ifndef MDZCUDA_H
+#define MDZCUDA_H
+
+#include <stdint.h>
+#include "mdz_mp_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* which reference line driver is being replaced */
+#define MDZCUDA_MODE_LD    0   /* fractal_calculate_line       src/fractal.c:29  (x87 long double)   */
+#define MDZCUDA_MODE_MPFR  1   /* fractal_mpfr_calculate_line  src/fractal.c:120 (MPFR, RNDN)        */
+#define MDZCUDA_MODE_GMP   2   /* fractal_gmp_calculate_line   src/fractal.c:260 (GMP mpf, truncate) */
+
+/* src/fractal.h:8-26 */
+#define MDZCUDA_FAMILY_MANDEL 0
+#define MDZCUDA_FAMILY_JULIA  1
+#define MDZCUDA_FRACTAL_MANDELBROT         0
+#define MDZCUDA_FRACTAL_BURNING_SHIP       1
+#define MDZCUDA_FRACTAL_GENERALIZED_CELTIC 2
+#define MDZCUDA_FRACTAL_VARIANT            3
+
+typedef struct mdzcuda_view {
+    int   mode;                 /* MDZCUDA_MODE_*  (image_info.c:238-248 picks the callback) */
+    long  precision;            /* img->precision, bits (ignored for MODE_LD)                */
+    int   family;               /* img->family                                               */
+    int   fractal;              /* img->fractal                                              */
+    long  depth;                /* img->depth, 1..INT32_MAX                                  */
+    int   real_width;           /* img->real_width  = user_width  * aa_factor                */
+    int   real_height;          /* img->real_height = user_height * aa_factor                */
+    int   aa_factor;            /* img->aa_factor, >= 1                                      */
+    /* MPFR rect as filled by coords_get_rect (render.c:34-35); LD mode reads
+     * xmin/xmax/ymax (fractal.c:50-53), MPFR mode xmin/ymax/width (fractal.c:160-170) */
+    const __mpfr_struct* xmin;
+    const __mpfr_struct* xmax;
+    const __mpfr_struct* ymax;
+    const __mpfr_struct* width;
+    /* GMP rect as filled by coords_get_rect_gmp (render.c:36-37; fractal.c:300-310) */
+    const __mpf_struct*  gxmin;
+    const __mpf_struct*  gymax;
+    const __mpf_struct*  gwidth;
+    /* img->u.julia.c_re / c_im, read only when family is julia (fractal.c:55-59,197-198,341-342) */
+    const __mpfr_struct* julia_re;
+    const __mpfr_struct* julia_im;
+} mdzcuda_view;
+
+typedef struct mdzcuda_plan mdzcuda_plan;
+
+/* Last error text for the calling thread ("" if none). */
+const char* mdzcuda_last_error(void);
+
+/* Number of CUDA devices visible; 0 (with an error text) if CUDA is unusable. */
+int mdzcuda_device_count(void);
+
+/*
+ * Build a render plan on one device: runs the O(W+H) host prologue (column
+ * and row coordinates computed with the same libmpfr / libgmp / long double
+ * operations the reference's line drivers use) and uploads the tables.
+ * The plan renders bands band_first, band_first+band_stride, ... where a band
+ * is aa_factor consecutive real lines (the unit rth_next_line hands out,
+ * src/render_threads.c:366-377).  band_first=0, band_stride=1 is the whole image.
+ * Returns NULL on failure.
+ */
+mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* view, int device,
+                                  int band_first, int band_stride);
+
+/* Tunables (before launch): iterations between queue refills (0 = default),
+ * resident blocks per SM (0 = occupancy maximum). */
+int mdzcuda_plan_tune(mdzcuda_plan*, int chunk_iters, int blocks_per_sm);
+
+/* Enqueue the reset + escape-time kernel on `cuda_stream` (a cudaStream_t; NULL
+ * = the legacy default stream).  Asynchronous. */
+int mdzcuda_plan_launch(mdzcuda_plan*, void* cuda_stream);
+
+/* Block until the last launch has finished. */
+int mdzcuda_plan_wait(mdzcuda_plan*);
+
+/* Ask a running launch to stop at its next poll (rth_ui_stop_render). */
+int mdzcuda_plan_cancel(mdzcuda_plan*);
+
+/* Bands completed so far by the current / last launch, and the plan's total. */
+int mdzcuda_plan_bands_done(mdzcuda_plan*);
+int mdzcuda_plan_bands_total(mdzcuda_plan*);
+
+/* Copy this plan's lines into a full-size host raw_data array
+ * (real_width*real_height int32, img->raw_data layout: line*real_width+ix). */
+int mdzcuda_plan_fetch(mdzcuda_plan*, int32_t* raw_host);
+
+/* Device pointer of the plan's iteration buffer ([local_lines][real_width] int32)
+ * and its line count, for callers that keep results on the GPU. */
+void* mdzcuda_plan_device_raw(mdzcuda_plan*);
+int   mdzcuda_plan_local_lines(mdzcuda_plan*);
+
+/* Static facts about the kernel chosen for this plan (for reports). */
+typedef struct mdzcuda_kernel_info {
+    int limbs;              /* 32-bit limbs of significand                */
+    int regs_per_thread;
+    int local_bytes;        /* spill / local memory per thread            */
+    int shared_bytes;       /* dynamic shared memory per block            */
+    int block_threads;
+    int blocks_per_sm;
+    int grid_blocks;
+    int sm_count;
+} mdzcuda_kernel_info;
+int mdzcuda_plan_kernel_info(mdzcuda_plan*, mdzcuda_kernel_info* out);
+
+void mdzcuda_plan_destroy(mdzcuda_plan*);
+
+/*
+ * One-call render: host view in, host raw_data out, over ndev devices
+ * (devices == NULL means 0..ndev-1), bands interleaved across devices.
+ * This is what the rth_* layer runs per render.  Returns 1 on success.
+ */
+int mdzcuda_render(const mdzcuda_view* view, int32_t* raw_host,
+                   int ndev, const int* devices);
+
+/*
+ * Measured integer-multiply peak of a device: runs a register-only
+ * IMAD.WIDE.U32 microbenchmark for about `ms` milliseconds and returns 32x32->64
+ * multiply-accumulates per second (the roofline denominator of SURVEY 8(d)).
+ */
+double mdzcuda_imad_peak(int device, int ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDZCUDA_H */

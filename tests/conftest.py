@@ -1,0 +1,38 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def emu_lib():
+    """Host build of the device arithmetic headers (tests/host_emu): test-only."""
+    import ctypes as C
+    src = os.path.join(ROOT, "tests", "host_emu", "emu.cpp")
+    out = os.path.join(ROOT, "tests", "host_emu", "libmdzemu.so")
+    deps = [src] + [os.path.join(ROOT, "mdz_b200", "csrc", f)
+                    for f in ("limb_ops.cuh", "mpfr_sf.cuh", "mp_convert.h", "mpf_sf.cuh")]
+    deps = [d for d in deps if os.path.exists(d)]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", out, src])
+    return C.CDLL(out)
+
+
+@pytest.fixture(scope="session")
+def ref_lib():
+    """The unmodified reference hot path (oracle/_ref/libmdzref.so).  Built in the
+    container from /root/reference; on the GPU box the prebuilt file is used."""
+    import refpath
+    lib = refpath.load()
+    if lib is None:
+        pytest.skip("oracle/_ref/libmdzref.so not available")
+    return lib

@@ -1,0 +1,52 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol the
+headers declare, and fails loudly (no fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:mdzcuda|rth)_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import mdz_b200
+    lib = C.CDLL(mdz_b200.LIB_PATH)
+    names = declared_symbols("mdzcuda.h")
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), n
+    rth = os.path.join(ROOT, "include", "mdz_rth.h")
+    if os.path.exists(rth):
+        for n in declared_symbols("mdz_rth.h"):
+            assert hasattr(lib, n), n
+
+
+def test_python_binding_covers_header():
+    from mdz_b200 import _native
+    assert sorted(_native.SYMBOLS) == declared_symbols("mdzcuda.h")
+
+
+def test_no_cpu_fallback_without_device():
+    import mdz_b200
+    from views import config2
+    if mdz_b200.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(mdz_b200.MdzCudaError):
+        mdz_b200.render(config2(16, 9, 10))
+    assert "CUDA" in mdz_b200.last_error() or "device" in mdz_b200.last_error()
+
+
+def test_bad_arguments_are_rejected():
+    import mdz_b200
+    from views import config2
+    v = config2(16, 9, 10)
+    v.depth = 0
+    with pytest.raises(mdz_b200.MdzCudaError):
+        mdz_b200.Plan(v)

@@ -1,0 +1,67 @@
+"""Named views used by the parity tests and bench.py."""
+from mdz_b200 import (ImageView, FAMILY_MANDEL, FAMILY_JULIA, MANDELBROT, BURNING_SHIP,
+                      GENERALIZED_CELTIC, VARIANT)
+from mdz_b200.coords import center_to_rect, rect_to_gmp
+from mdz_b200.mp import Mpfr
+
+
+def make_view(cx, cy, size, w, h, *, mode="mpfr", precision=80, depth=300, aa=1,
+              family=FAMILY_MANDEL, fractal=MANDELBROT, julia=None, fixed_re=True):
+    """Centre/size view the way MDZ's host would hand it to the render pool."""
+    xmin, xmax, ymax, width, crect = center_to_rect(cx, cy, size, w, h, precision)
+    v = ImageView(use_multi_prec=(mode != "ld"), use_rounding=(mode == "mpfr"),
+                  precision=precision, family=family, fractal=fractal, depth=depth,
+                  user_width=w, user_height=h, aa_factor=aa,
+                  xmin=xmin, xmax=xmax, ymax=ymax, width=width)
+    if mode == "gmp":
+        v.gxmin, v.gymax, v.gwidth = rect_to_gmp(crect, precision, fixed_re)
+    if julia is not None:
+        ip = max(precision, 80)
+        v.julia_re, v.julia_im = Mpfr(ip, julia[0]), Mpfr(ip, julia[1])
+    return v
+
+
+# BASELINE.json configs[1]: full M-set, "double" (= long double) precision, maxiter 10k
+def config2(w=1920, h=1080, depth=10000):
+    return make_view("-0.5", "0.0", "4.0", w, h, mode="ld", depth=depth)
+
+
+SEAHORSE = ("-0.743643887037158704752191506114774", "0.131825904205311970493132056385139")
+
+
+def rect_view(xmin, xmax, ymax, w, h, *, mode="mpfr", precision=80, depth=300, aa=1,
+              family=FAMILY_MANDEL, fractal=MANDELBROT):
+    """A view given directly as the rect the hot path reads (img->xmin, xmax,
+    ymax; width = RN(xmax - xmin) as coords_rect_to_center computes it)."""
+    from mdz_b200.mp import mpfr
+    ip = max(precision, 80)
+    a, b, c = Mpfr(ip, xmin), Mpfr(ip, xmax), Mpfr(ip, ymax)
+    wd = Mpfr(ip)
+    mpfr.mpfr_sub(wd.ref, b.ref, a.ref, 0)
+    return ImageView(use_multi_prec=(mode != "ld"), use_rounding=(mode == "mpfr"),
+                     precision=precision, family=family, fractal=fractal, depth=depth,
+                     user_width=w, user_height=h, aa_factor=aa,
+                     xmin=a, xmax=b, ymax=c, width=wd)
+
+
+# gallery/deep_embedded_julia.mdz as its author meant it:
+# MPFR-320, depth 10000, a 3.79e-39 wide window
+DEEP_EMBEDDED_JULIA = dict(
+    xmin="-1.9990958622795566830287308905472659490602008969484573074469166957563201773778385691107409249442388",
+    xmax="-1.9990958622795566830287308905472659490564113825918759307447952539214217882449639333585621571026900",
+    ymax="1.2251442643252650599959235781025334506324529252744858584464673344525174648352769071170032669073514e-5")
+
+
+def deep_embedded_julia(w=1920, h=1080, depth=10000, precision=320):
+    d = DEEP_EMBEDDED_JULIA
+    return rect_view(d["xmin"], d["xmax"], d["ymax"], w, h, precision=precision, depth=depth)
+
+
+# gallery/honeytrace.mdz: MPFR-176, depth 25000
+HONEYTRACE = ("-7.66701995256949964922178305994168934712886433081717606e-1",
+              "1.00264595952135512543352958560880514410135965558537508e-1",
+              "2.94676302638774725686015831604561721063962123995835471e-19")
+
+
+def honeytrace(w=96, h=72, depth=25000):
+    return make_view(HONEYTRACE[0], HONEYTRACE[1], HONEYTRACE[2], w, h, precision=176, depth=depth)
