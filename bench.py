@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- pixel-iterations/s of the escape-time path on B200.
+
+One "step" is one complete render of the workload view (reset queue + the
+persistent escape-time kernel).  At N=1 the workload is BASELINE.json
+configs[1]: the full Mandelbrot set, 1920x1080, MDZ's hardware-precision mode
+(x87 long double == 64-bit significand, SURVEY finding 1), depth 10000.  With N
+ranks (torchrun, one process per GPU) the same image is split into interleaved
+line bands, one plan per rank, no data-path collective ("strong" scaling).
+
+Prints ONE JSON line (rank 0).  `--impl reference` instead times the unmodified
+reference's own pthread pool (oracle/_ref/libmdzref.so) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "pixel_iterations_per_sec"
+UNIT = "pixel-iterations/s"
+
+
+def macs_per_iteration(n_limbs):
+    """one general product N^2 + two squarings N(N+1)/2 each."""
+    return 2 * n_limbs * n_limbs + n_limbs
+
+
+def workload_view():
+    from views import config2
+    return config2(1920, 1080, 10000)
+
+
+def iterations_of(raw, depth):
+    import numpy as np
+    return int(np.where(raw > 0, raw, depth).astype(np.int64).sum())
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for k, n in enumerate(names):
+                if r[5 + k].lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args):
+    """Reference arm: the unmodified reference pool on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import refpath
+    from views import config2
+    lib = refpath.load()
+    cores = os.cpu_count() or 1
+    # bounded sample: the same view at half resolution each way (same set, 1/4 of the pixels)
+    view = config2(960, 540, 10000)
+    kind = "reference"
+    if lib is None:
+        import portpath
+        kind = "port"
+    times, iters = [], 0
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        if lib is not None:
+            raw, _ = refpath.ref_render(lib, view, cores)
+        else:
+            raw = portpath.port_render(view, cores)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+            iters = iterations_of(raw, view.depth)
+    total = sum(times)
+    value = iters * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "x87 long double (64-bit significand)",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: full M-set, long double, depth 10000 "
+                               "(sample rendered at 960x540)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "same view at 960x540 (1/4 of the pixels), %d pixel-iterations per step, "
+                                   "reference pthread pool with -t %d" % (iters, cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def side_precisions(torch, device):
+    """Kernel-only it/s at the other precisions of the metric, on bounded views."""
+    import mdz_b200
+    from views import make_view, SEAHORSE, deep_embedded_julia
+    out = {}
+    cases = [
+        ("mpfr128", make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", 1920, 1080, precision=128, depth=10000)),
+        ("mpfr320", deep_embedded_julia(960, 540)),
+        ("mpfr512", make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", 960, 540, precision=512, depth=10000)),
+    ]
+    peak = mdz_b200.imad_peak(device, 100)
+    for name, view in cases:
+        plan = mdz_b200.Plan(view, device)
+        st = torch.cuda.current_stream().cuda_stream
+        plan.launch(st); plan.wait()                    # warm-up
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); plan.launch(st); e1.record(); e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        iters = iterations_of(plan.fetch(), view.depth)
+        ki = plan.kernel_info()
+        rate = iters / (ms * 1e-3)
+        out[name] = {"value": rate, "unit": UNIT, "ms": ms, "pixel_iterations": iters,
+                     "view": "%dx%d" % (view.real_width, view.real_height),
+                     "limbs": ki["limbs"], "regs": ki["regs_per_thread"], "spill_bytes": ki["local_bytes"],
+                     "blocks_per_sm": ki["blocks_per_sm"],
+                     "imad_frac": rate * macs_per_iteration(ki["limbs"]) / peak}
+        plan.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-side", action="store_true", help="skip the per-precision side measurements")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import mdz_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    view = workload_view()
+    plan = mdz_b200.Plan(view, local, band_first=rank, band_stride=world)
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        plan.launch(stream)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0.record()
+    for i in range(args.steps):
+        flush.zero_()
+        kev[i][0].record()
+        plan.launch(stream)
+        kev[i][1].record()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    raw = plan.fetch()
+    my_lines = raw[[l for b in range(rank, view.user_height, world)
+                    for l in range(b * view.aa_factor, (b + 1) * view.aa_factor)]]
+    my_iters = iterations_of(my_lines, view.depth)
+    t = torch.tensor([ms_total, kernel_ms], dtype=torch.float64, device="cuda")
+    it = torch.tensor([my_iters], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(it, op=dist.ReduceOp.SUM)
+    ms_total, kernel_ms = float(t[0]), float(t[1])
+    total_iters = int(it[0])
+    value = total_iters * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end through the public call: host view in, host raw_data out ----
+    xs_bytes = (plan.kernel_info()["limbs"] + 2) * 4 * (view.real_width + plan.local_lines() + 2)
+    e2e_steps = max(1, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        p2 = mdz_b200.Plan(view, local, band_first=rank, band_stride=world)   # prologue + H2D
+        p2.launch(stream)
+        out = p2.fetch()                                                         # sync + D2H
+        p2.close()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_iters * e2e_steps / float(te[0])
+    assert np.array_equal(out[rank * view.aa_factor], raw[rank * view.aa_factor])
+
+    if rank == 0:
+        ki = plan.kernel_info()
+        peak = mdz_b200.imad_peak(local, 200)
+        macs = macs_per_iteration(ki["limbs"])
+        kernel_rate = (total_iters / world) / (kernel_ms * 1e-3)        # this GPU's kernel alone
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 limbs (64-bit significand soft-float == x87 long double)",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: full M-set cx=-0.5 cy=0 size=4, 1920x1080, "
+                                   "long double mode, depth 10000",
+                       "pixel_iterations_per_step": total_iters,
+                       "partition": "interleaved line bands, one plan per rank, no collective",
+                       "l2": "256 MiB buffer rewritten between steps (inputs are KB-sized tables)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps,
+                    "h2d_bytes_per_step": xs_bytes, "d2h_bytes_per_step": int(my_lines.nbytes),
+                    "includes": "host prologue (libmpfr/long double tables), H2D, kernel, D2H of raw_data"},
+            "gpu_launches": args.steps * world,
+            "clocks": clocks,
+            "roofline": {"bound": "imad", "achieved": kernel_rate * macs / 1e12, "peak": peak / 1e12,
+                         "unit": "T 32x32->64 MAC/s", "frac": kernel_rate * macs / peak,
+                         "traffic": None,
+                         "note": "achieved = it/s x W(N)=2N^2+N MACs (N=%d limbs -> %d); peak = IMAD.WIDE.U32 "
+                                 "microbenchmark measured in this run (MEASURED_PEAKS.json has no integer peak); "
+                                 "kernel avg launch %.3f ms by CUDA events" % (ki["limbs"], macs, kernel_ms)},
+            "kernel": ki,
+        }
+        # CPU baseline: the unmodified reference pool on this box's cores, bounded sample
+        try:
+            import refpath
+            from views import config2
+            lib = refpath.load()
+            cores = os.cpu_count() or 1
+            sample = config2(960, 540, 10000)
+            t0 = time.perf_counter()
+            rraw, _ = refpath.ref_render(lib, sample, cores)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": iterations_of(rraw, sample.depth) / dt, "unit": UNIT,
+                                    "cores": cores, "kind": "reference",
+                                    "sample": "same view at 960x540, unmodified reference pool, -t %d, %.2f s" % (cores, dt)}
+        except Exception as ex:   # the reference .so is optional on the box
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)}
+        if not args.no_side and world == 1:
+            line["per_precision"] = side_precisions(torch, local)
+        print(json.dumps(line))
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
