@@ -15,12 +15,9 @@
 // Every `chunk` iterations a warp refills its finished lanes with one
 // warp-aggregated atomicAdd.
 #pragma once
-#include "mpfr_sf.cuh"
+#include "escape_step.cuh"
 
 namespace mdz {
-
-enum { FRACTAL_MANDELBROT = 0, FRACTAL_BURNING_SHIP = 1, FRACTAL_GENERALIZED_CELTIC = 2, FRACTAL_VARIANT = 3 };
-enum { FAMILY_MANDEL = 0, FAMILY_JULIA = 1 };
 
 // Column / row tables, limb-major so that lanes on neighbouring pixels coalesce.
 //   m[k * count + i]  limb k (0 = least significant) of entry i
@@ -64,26 +61,34 @@ __device__ __forceinline__ void load_entry(const CoordTable& t, int i, Num<N>& v
     v.s = __ldg(&t.s[i]);
 }
 
+// resident blocks per SM the register allocator is asked to make room for
+template <int N> struct MinBlocks {
+    static constexpr int value = N <= 3 ? 8 : N <= 5 ? 6 : N <= 8 ? 5 : N <= 12 ? 4 : 3;
+};
+
 template <int N>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, MinBlocks<N>::value)
 escape_mpfr_kernel(const EscapeParams p)
 {
     // per-thread copy of c (2N limbs), limb-major: conflict-free
     extern __shared__ uint32_t csm[];
     uint32_t* cre_m = csm + threadIdx.x;
     uint32_t* cim_m = csm + N * kBlock + threadIdx.x;
+    // limb-shifter scratch column (mpfr_sf.cuh shift_right_far): upper half stays zero
+    uint32_t* scr = csm + 2 * N * kBlock + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < ScratchWords<N>::value; ++k) scr[k * kBlock] = 0u;
+    static_assert(kScratchStride == kBlock, "scratch stride must equal the block size");
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned total = (unsigned)p.width * (unsigned)p.lines;
 
-    Num<N> wre, wim, wre2, wim2;
-    int32_t cre_e = E_ZERO, cim_e = E_ZERO;
-    uint32_t cre_s = 0, cim_s = 0;
-    set_zero(wre); set_zero(wim); set_zero(wre2); set_zero(wim2);
+    PixelState<N> st;
+    set_zero(st.wre); set_zero(st.wim); set_zero(st.wre2); set_zero(st.wim2);
+    st.cre_e = E_ZERO; st.cim_e = E_ZERO; st.cre_s = 0; st.cim_s = 0; st.iter = 0;
 
     bool active = false;
     bool exhausted = false;         // warp-uniform
-    int iter = 0;
     unsigned pix = 0;
 
     const bool abs_im = p.fractal == FRACTAL_BURNING_SHIP;
@@ -111,20 +116,14 @@ escape_mpfr_kernel(const EscapeParams p)
                         pix = idx;
                         const int line = (int)(idx / (unsigned)p.width);
                         const int ix = (int)(idx - (unsigned)line * (unsigned)p.width);
-                        Num<N> x, y;
+                        Num<N> x, y, cx, cy;
                         load_entry<N>(p.xs, ix, x);
                         load_entry<N>(p.ys, line, y);
-                        wre = x; wim = y;
-                        fsqr<N>(x, wre2, p.rc);
-                        fsqr<N>(y, wim2, p.rc);
                         if (p.family == FAMILY_JULIA) {
-                            load_entry<N>(p.jc, 0, x);
-                            load_entry<N>(p.jc, 1, y);
-                        }
-#pragma unroll
-                        for (int k = 0; k < N; ++k) { cre_m[k * kBlock] = x.m[k]; cim_m[k * kBlock] = y.m[k]; }
-                        cre_e = x.e; cre_s = x.s; cim_e = y.e; cim_s = y.s;
-                        iter = 0;
+                            load_entry<N>(p.jc, 0, cx);
+                            load_entry<N>(p.jc, 1, cy);
+                        } else { cx = x; cy = y; }
+                        pixel_init<N>(st, x, y, cx, cy, p.rc, cre_m, cim_m);
                         active = true;
                     }
                 }
@@ -135,33 +134,8 @@ escape_mpfr_kernel(const EscapeParams p)
         // ---- iterate ------------------------------------------------------
         for (int k = 0; k < p.chunk; ++k) {
             if (active) {
-                ++iter;
-                Num<N> t, c;
-                // wim = 2*wre*wim + c_im       (|.| on the product for burning ship)
-                fmul<N>(wre, wim, t, p.rc);
-                if (t.m[N - 1] != 0) t.e += 1;
-                if (abs_im) t.s = 0;
-#pragma unroll
-                for (int q = 0; q < N; ++q) c.m[q] = cim_m[q * kBlock];
-                c.e = cim_e; c.s = cim_s;
-                fadd<N, MODE_GENERIC>(t, c, wim, p.rc);
-                // wre = wre2 - wim2 + c_re     (|.| on the difference for celtic / odd steps of the hybrid)
-                fadd<N, MODE_SUB_POS>(wre2, wim2, t, p.rc);
-                if (abs_re == 1 || (abs_re == 2 && (iter & 1))) t.s = 0;
-#pragma unroll
-                for (int q = 0; q < N; ++q) c.m[q] = cre_m[q * kBlock];
-                c.e = cre_e; c.s = cre_s;
-                fadd<N, MODE_GENERIC>(t, c, wre, p.rc);
-                fsqr<N>(wim, wim2, p.rc);
-                fsqr<N>(wre, wre2, p.rc);
-                // escape: RN(wim2 + wre2) > 4.  Both < 2 cannot exceed 4 even
-                // after rounding; either >= 8 certainly does.
-                const int32_t emax = wim2.e > wre2.e ? wim2.e : wre2.e;
-                bool esc = emax >= 4;
-                if (!esc && emax >= 2) {
-                    fadd<N, MODE_ADD_POS>(wim2, wre2, t, p.rc);
-                    esc = greater_than_4<N>(t);
-                }
+                const bool esc = pixel_step<N>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re);
+                const int iter = st.iter;
                 if (esc || iter >= p.depth) {
                     p.raw[pix] = esc ? iter : 0;
                     __threadfence();            // raw visible before the band counter moves

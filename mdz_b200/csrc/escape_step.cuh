@@ -1,0 +1,80 @@
+// escape_step.cuh -- one pixel's state and one iteration of the escape-time
+// recurrence, MPFR-faithful.  Shared by the CUDA kernel (escape_kernel.cuh) and,
+// compiled for the host with MDZ_HOST_EMU, by the CPU-side tests.
+//
+// pixel_step restates the loop body of the reference's frac_mandel_mpfr
+// (src/frac_mandel.c:34-50) and its three variants: frac_burning_ship_mpfr
+// takes |.| of the rounded product (src/frac_burning_ship.c:38-41),
+// frac_generalized_celtic_mpfr of the rounded difference
+// (src/frac_generalized_celtic.c:42-44), frac_variant_mpfr of the difference on
+// odd iterations only (src/frac_variant.c:42-43).
+#pragma once
+#include "mpfr_sf.cuh"
+
+namespace mdz {
+
+enum { FRACTAL_MANDELBROT = 0, FRACTAL_BURNING_SHIP = 1, FRACTAL_GENERALIZED_CELTIC = 2, FRACTAL_VARIANT = 3 };
+enum { FAMILY_MANDEL = 0, FAMILY_JULIA = 1 };
+
+template <int N>
+struct PixelState {
+    Num<N> wre, wim, wre2, wim2;
+    int32_t cre_e, cim_e;       // c's limbs live in a per-thread shared-memory column
+    uint32_t cre_s, cim_s;
+    int iter;
+};
+
+// set-up of one pixel (reference src/fractal.c:188-203): z0 = (x, y), squares
+// rounded once, c = pixel (Mandelbrot family) or the Julia constant.
+template <int N>
+MDZ_HD void pixel_init(PixelState<N>& st, const Num<N>& x, const Num<N>& y,
+                       const Num<N>& cx, const Num<N>& cy, const RoundCfg& rc,
+                       uint32_t* cre_m, uint32_t* cim_m)
+{
+    st.wre = x; st.wim = y;
+    fsqr<N>(x, st.wre2, rc);
+    fsqr<N>(y, st.wim2, rc);
+    MDZ_UNROLL
+    for (int k = 0; k < N; ++k) { cre_m[k * kScratchStride] = cx.m[k]; cim_m[k * kScratchStride] = cy.m[k]; }
+    st.cre_e = cx.e; st.cre_s = cx.s; st.cim_e = cy.e; st.cim_s = cy.s;
+    st.iter = 0;
+}
+
+// one iteration; returns true when RN(wim2 + wre2) > 4 (the pixel escaped at st.iter)
+template <int N>
+MDZ_HD bool pixel_step(PixelState<N>& st, const uint32_t* cre_m, const uint32_t* cim_m,
+                       uint32_t* scr, const RoundCfg& rc, bool abs_im, int abs_re)
+{
+    ++st.iter;
+    MDZ_COUNT(CNT_ITER);
+    Num<N> t, c;
+    // wim = 2*wre*wim + c_im       (|.| on the product for burning ship)
+    fmul<N>(st.wre, st.wim, t, rc);
+    if (t.m[N - 1] != 0) t.e += 1;
+    if (abs_im) t.s = 0;
+    MDZ_UNROLL
+    for (int q = 0; q < N; ++q) c.m[q] = cim_m[q * kScratchStride];
+    c.e = st.cim_e; c.s = st.cim_s;
+    fadd<N, MODE_GENERIC>(t, c, st.wim, rc, scr);
+    // wre = wre2 - wim2 + c_re     (|.| on the difference for celtic / odd steps of the hybrid)
+    fadd<N, MODE_SUB_POS>(st.wre2, st.wim2, t, rc, scr);
+    if (abs_re == 1 || (abs_re == 2 && (st.iter & 1))) t.s = 0;
+    MDZ_UNROLL
+    for (int q = 0; q < N; ++q) c.m[q] = cre_m[q * kScratchStride];
+    c.e = st.cre_e; c.s = st.cre_s;
+    fadd<N, MODE_GENERIC>(t, c, st.wre, rc, scr);
+    fsqr<N>(st.wim, st.wim2, rc);
+    fsqr<N>(st.wre, st.wre2, rc);
+    // escape: RN(wim2 + wre2) > 4.  Both < 2 cannot exceed 4 even after
+    // rounding; either >= 8 certainly does.
+    const int32_t emax = st.wim2.e > st.wre2.e ? st.wim2.e : st.wre2.e;
+    bool esc = emax >= 4;
+    if (!esc && emax >= 2) {
+        MDZ_COUNT(CNT_ESC_ADD);
+        fadd<N, MODE_ADD_POS>(st.wim2, st.wre2, t, rc, scr);
+        esc = greater_than_4<N>(t);
+    }
+    return esc;
+}
+
+}  // namespace mdz

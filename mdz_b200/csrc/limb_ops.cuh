@@ -24,6 +24,16 @@
 
 namespace mdz {
 
+// path counters: compiled in for the host emulation only (tests/host_emu)
+#if defined(MDZ_HOST_EMU)
+enum { CNT_ADD_FAST, CNT_ADD_MEDIUM, CNT_ADD_COPY, CNT_ADD_TIE, CNT_ADD_CANCEL, CNT_ROUND_CARRY,
+       CNT_MUL_BAIL, CNT_ESC_ADD, CNT_ITER, CNT_N };
+static thread_local unsigned long long g_counts[CNT_N];
+#define MDZ_COUNT(id) (++::mdz::g_counts[::mdz::id])
+#else
+#define MDZ_COUNT(id) ((void)0)
+#endif
+
 #if defined(MDZ_HOST_EMU)
 static thread_local uint32_t g_cc = 0;
 inline uint32_t add_cc(uint32_t a, uint32_t b)
@@ -188,6 +198,111 @@ MDZ_HD void sqr_full(const uint32_t (&a)[N], uint32_t (&r)[2 * N])
     mad_wide_cc(r[0], r[1], a[0], a[0]);
     MDZ_UNROLL
     for (int i = 1; i < N; ++i) madc_wide_cc(r[2 * i], r[2 * i + 1], a[i], a[i]);
+}
+
+
+// ---------------------------------------------------------------------------
+// High part of the product: t[0..N+1] = sum over i+j >= N-2 of
+// a[i]*b[j] * 2^(32*(i+j-(N-2))), i.e. limb positions N-2 .. 2N-1 of the full
+// product without the carries from the columns below.  N(N+1)/2 + 2N - 1
+// IMAD.WIDE instead of N^2.  The omitted columns sum to less than
+// (N-1) * 2^(32*(N-1)): fewer than N units of t[1]'s least significant bit.
+// MPFR itself uses such a "mulhigh" and falls back to the full product when the
+// rounding cannot be decided; so does the caller here (mpfr_sf.cuh).
+// Same even/odd accumulator scheme as mul_full, indexed by q = i+j-(N-2).
+// ---------------------------------------------------------------------------
+template <int N>
+MDZ_HD void mul_hi(const uint32_t (&a)[N], const uint32_t (&b)[N], uint32_t (&t)[N + 2])
+{
+    uint32_t e[N + 4], o[N + 4];
+    MDZ_UNROLL
+    for (int i = 0; i < N + 4; ++i) { e[i] = 0; o[i] = 0; }
+    MDZ_UNROLL
+    for (int i = 0; i < N; ++i) {
+        const int jmin = (N - 2 - i) > 0 ? (N - 2 - i) : 0;
+        MDZ_UNROLL
+        for (int c = 0; c < 2; ++c) {
+            if (jmin + c >= N) continue;
+            int last = 0;
+            MDZ_UNROLL
+            for (int j = jmin + c; j < N; j += 2) {
+                const int q = i + j - (N - 2);
+                if ((q & 1) == 0) {
+                    if (j == jmin + c) mad_wide_cc(e[q], e[q + 1], a[j], b[i]);
+                    else               madc_wide_cc(e[q], e[q + 1], a[j], b[i]);
+                } else {
+                    if (j == jmin + c) mad_wide_cc(o[q - 1], o[q], a[j], b[i]);
+                    else               madc_wide_cc(o[q - 1], o[q], a[j], b[i]);
+                }
+                last = q;
+            }
+            const int cp = last + 2;
+            if (cp < N + 2) {
+                if ((cp & 1) == 0) e[cp] = addc(e[cp], 0u);
+                else               o[cp - 1] = addc(o[cp - 1], 0u);
+            }
+        }
+    }
+    t[0] = e[0];
+    t[1] = add_cc(e[1], o[0]);
+    MDZ_UNROLL
+    for (int i = 2; i < N + 1; ++i) t[i] = addc_cc(e[i], o[i - 1]);
+    t[N + 1] = addc(e[N + 1], o[N]);
+}
+
+// High part of the square, same contract as mul_hi.
+template <int N>
+MDZ_HD void sqr_hi(const uint32_t (&a)[N], uint32_t (&t)[N + 2])
+{
+    uint32_t e[N + 4], o[N + 4];
+    MDZ_UNROLL
+    for (int i = 0; i < N + 4; ++i) { e[i] = 0; o[i] = 0; }
+    MDZ_UNROLL
+    for (int i = 0; i < N - 1; ++i) {
+        const int jmin = (N - 2 - i) > (i + 1) ? (N - 2 - i) : (i + 1);
+        MDZ_UNROLL
+        for (int c = 0; c < 2; ++c) {
+            if (jmin + c >= N) continue;
+            int last = 0;
+            MDZ_UNROLL
+            for (int j = jmin + c; j < N; j += 2) {
+                const int q = i + j - (N - 2);
+                if ((q & 1) == 0) {
+                    if (j == jmin + c) mad_wide_cc(e[q], e[q + 1], a[j], a[i]);
+                    else               madc_wide_cc(e[q], e[q + 1], a[j], a[i]);
+                } else {
+                    if (j == jmin + c) mad_wide_cc(o[q - 1], o[q], a[j], a[i]);
+                    else               madc_wide_cc(o[q - 1], o[q], a[j], a[i]);
+                }
+                last = q;
+            }
+            const int cp = last + 2;
+            if (cp < N + 2) {
+                if ((cp & 1) == 0) e[cp] = addc(e[cp], 0u);
+                else               o[cp - 1] = addc(o[cp - 1], 0u);
+            }
+        }
+    }
+    uint32_t x[N + 2];
+    x[0] = e[0];
+    x[1] = add_cc(e[1], o[0]);
+    MDZ_UNROLL
+    for (int i = 2; i < N + 1; ++i) x[i] = addc_cc(e[i], o[i - 1]);
+    x[N + 1] = addc(e[N + 1], o[N]);
+    MDZ_UNROLL
+    for (int i = N + 1; i >= 1; --i) t[i] = fsl(x[i - 1], x[i], 1);
+    t[0] = x[0] << 1;
+    // diagonal a[i]^2 at position 2i >= N-2: q = 2i-(N-2), consecutive pairs
+    constexpr int i0 = (N - 1) / 2;          // smallest i with 2i >= N-2
+    {
+        constexpr int q0 = 2 * i0 - (N - 2);
+        mad_wide_cc(t[q0], t[q0 + 1], a[i0], a[i0]);
+    }
+    MDZ_UNROLL
+    for (int i = i0 + 1; i < N; ++i) {
+        const int q = 2 * i - (N - 2);
+        madc_wide_cc(t[q], t[q + 1], a[i], a[i]);
+    }
 }
 
 }  // namespace mdz

@@ -280,7 +280,7 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
         CUDA_OKP(cudaFuncGetAttributes(&fa, (const void*)fn));
         cudaDeviceProp prop;
         CUDA_OKP(cudaGetDeviceProperties(&prop, device));
-        const int smem = 2 * n32 * kBlock * (int)sizeof(uint32_t);
+        const int smem = (4 * n32 + 2) * kBlock * (int)sizeof(uint32_t);   // c_re, c_im, shifter scratch
         if (smem > 48 * 1024)
             CUDA_OKP(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ = 0;

@@ -6,7 +6,7 @@
 // without a GPU.  It is not a product path: libmdzcuda never links this file
 // and has no CPU fallback.
 #define MDZ_HOST_EMU 1
-#include "../../mdz_b200/csrc/mpfr_sf.cuh"
+#include "../../mdz_b200/csrc/escape_step.cuh"
 #include "../../mdz_b200/csrc/mp_convert.h"
 
 using namespace mdz;
@@ -19,15 +19,16 @@ static int binop(int op, long prec,
 {
     RoundCfg rc = make_round_cfg(N, (int)prec);
     Num<N> a, b, r;
+    uint32_t scratch[ScratchWords<N>::value] = {0};
     if (as == 0) set_zero(a); else { sig64_to_sig32(al, prec, a.m, N); a.e = (int32_t)ae; a.s = as < 0; }
     if (bs == 0) set_zero(b); else { sig64_to_sig32(bl, prec, b.m, N); b.e = (int32_t)be; b.s = bs < 0; }
     switch (op) {
     case 0: fmul<N>(a, b, r, rc); break;
     case 1: fsqr<N>(a, r, rc); break;
-    case 2: fadd<N, MODE_GENERIC>(a, b, r, rc); break;
-    case 3: b.s ^= 1u; fadd<N, MODE_GENERIC>(a, b, r, rc); break;
-    case 4: fadd<N, MODE_SUB_POS>(a, b, r, rc); break;
-    case 5: fadd<N, MODE_ADD_POS>(a, b, r, rc); break;
+    case 2: fadd<N, MODE_GENERIC>(a, b, r, rc, scratch); break;
+    case 3: b.s ^= 1u; fadd<N, MODE_GENERIC>(a, b, r, rc, scratch); break;
+    case 4: fadd<N, MODE_SUB_POS>(a, b, r, rc, scratch); break;
+    case 5: fadd<N, MODE_ADD_POS>(a, b, r, rc, scratch); break;
     case 6: *rs = greater_than_4<N>(a) ? 1 : 0; return 1;
     default: return 0;
     }
@@ -49,4 +50,46 @@ extern "C" int emu_binop(int op, long prec,
     CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16) CASE(20) CASE(24) CASE(32)
     default: return 0;
     }
+}
+
+
+// ---- whole-pixel emulation: the kernel's pixel_init / pixel_step on the host ----
+template <int N>
+static long pixel(long prec, int fractal, long depth,
+                  const uint64_t* const* l, const int* sg, const long* ex)
+{
+    RoundCfg rc = make_round_cfg(N, (int)prec);
+    Num<N> v[4];        // x, y, cx, cy
+    for (int k = 0; k < 4; ++k) {
+        if (sg[k] == 0) set_zero(v[k]);
+        else { sig64_to_sig32(l[k], prec, v[k].m, N); v[k].e = (int32_t)ex[k]; v[k].s = sg[k] < 0; }
+    }
+    uint32_t cre[N], cim[N], scr[ScratchWords<N>::value] = {0};
+    PixelState<N> st;
+    pixel_init<N>(st, v[0], v[1], v[2], v[3], rc, cre, cim);
+    const bool abs_im = fractal == FRACTAL_BURNING_SHIP;
+    const int abs_re = fractal == FRACTAL_GENERALIZED_CELTIC ? 1 : fractal == FRACTAL_VARIANT ? 2 : 0;
+    while (st.iter < depth)
+        if (pixel_step<N>(st, cre, cim, scr, rc, abs_im, abs_re)) return st.iter;
+    return 0;
+}
+
+#define PCASE(n) case n: return pixel<n>(prec, fractal, depth, l, sg, ex);
+extern "C" long emu_pixel(long prec, int fractal, long depth,
+                          const uint64_t* xl, int xs, long xe, const uint64_t* yl, int ys, long ye,
+                          const uint64_t* cxl, int cxs, long cxe, const uint64_t* cyl, int cys, long cye)
+{
+    const uint64_t* l[4] = {xl, yl, cxl, cyl};
+    const int sg[4] = {xs, ys, cxs, cys};
+    const long ex[4] = {xe, ye, cxe, cye};
+    switch (limbs32_for_prec(prec)) {
+    PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(6) PCASE(7) PCASE(8) PCASE(9) PCASE(10)
+    PCASE(11) PCASE(12) PCASE(13) PCASE(14) PCASE(15) PCASE(16) PCASE(20) PCASE(24) PCASE(32)
+    default: return -1;
+    }
+}
+
+extern "C" void emu_counts(unsigned long long* out, int reset)
+{
+    for (int i = 0; i < CNT_N; ++i) { out[i] = g_counts[i]; if (reset) g_counts[i] = 0; }
 }

@@ -130,3 +130,53 @@ def test_greater_than_4(emu):
         sa, ea, _ = a.parts()
         emu.emu_binop(6, prec, al, sa, ea, al, sa, ea, (C.c_uint64 * n)(), C.byref(rs), C.byref(C.c_long()))
         assert rs.value == (1 if mpfr.mpfr_greater_p(a.ref, four.ref) else 0), a.parts()
+
+
+def _sqrt_mod_2k(L, k):
+    """x with x*x == L (mod 2^k) for L == 1 (mod 8), by lifting one bit at a time."""
+    x = 1
+    for b in range(3, k):
+        if (x * x - L) >> b & 1:
+            x += 1 << (b - 1)
+    assert (x * x - L) % (1 << k) == 0
+    return x
+
+
+@pytest.mark.parametrize("prec", [64, 80, 128, 176, 320, 512])
+def test_products_next_to_rounding_boundaries(emu, prec):
+    """The fast path rounds from a truncated (high-part) product and falls back
+    to the full product when the decision is within the truncation error of a
+    boundary.  Build operands whose exact 2p-bit product has the bits below the
+    rounding position a few guard-limb units from wrapping / from zero, with
+    random low limbs, so the truncated sum really differs from the true one."""
+    rng = random.Random(4242 + prec)
+    n32 = (prec + 31) // 32
+    unit = 1 << max(0, 32 * (n32 - 1) - (32 * n32 - prec) - 1)   # ~ one guard-limb ulp in product bits
+    four = 0
+    for trial in range(1200):
+        w = prec - 1 - rng.randrange(2)            # width of the field below the round bit (sh = 0 / 1)
+        delta = rng.randrange(0, 5 * n32 + 12)
+        lowrand = rng.getrandbits(max(1, unit.bit_length() - 1)) if rng.randrange(4) else 0
+        if rng.randrange(2):
+            B = ((1 << w) - delta * unit - lowrand) % (1 << w)      # about to wrap
+        else:
+            B = (delta * unit + lowrand) % (1 << w)                  # just above zero
+        L = B | (rng.getrandbits(1) << w)                           # the round bit itself
+        if trial % 3 == 0:
+            # square: a*a == L (mod 2^(p-1)) needs L == 1 (mod 8)
+            L = (L & ~7) | 1
+            a = _sqrt_mod_2k(L % (1 << (prec - 1)), prec - 1)
+            if rng.randrange(2):
+                a = (-a) % (1 << (prec - 1))
+            a |= 1 << (prec - 1)
+            b = a
+        else:
+            a = rand_mant(rng, prec) | 1
+            b = (L * pow(a, -1, 1 << prec)) % (1 << (prec - 1)) | (1 << (prec - 1))
+        A = Mpfr(prec).set_parts(1, rng.randrange(-3, 3), a)
+        Bv = Mpfr(prec).set_parts(rng.choice([1, -1]), rng.randrange(-3, 3), b)
+        assert emu_op(emu, 0, prec, A, Bv) == mpfr_op("mul", prec, A, Bv), (hex(a), hex(b))
+        if a == b:
+            assert emu_op(emu, 1, prec, A, A) == mpfr_op("sqr", prec, A, A), hex(a)
+            four += 1
+    assert four > 100

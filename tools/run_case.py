@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Run one named render case once or a few times (for ncu / quick timing)."""
+import argparse
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import mdz_b200
+from views import make_view, config2, SEAHORSE, deep_embedded_julia
+
+
+def case(name, scale=1.0):
+    w, h = int(960 * scale), int(540 * scale)
+    if name == "ld":
+        return config2(2 * w, 2 * h, 10000)
+    if name.startswith("mpfr"):
+        p = int(name[4:])
+        if p == 320:
+            return deep_embedded_julia(w, h)
+        return make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", w, h, precision=p, depth=10000)
+    if name.startswith("sea"):
+        return make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", w, h, precision=int(name[3:]), depth=10000)
+    if name.startswith("dej"):
+        return deep_embedded_julia(w, h, precision=int(name[3:]))
+    raise SystemExit("unknown case " + name)
+
+
+ap = argparse.ArgumentParser()
+ap.add_argument("case")
+ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--scale", type=float, default=1.0)
+ap.add_argument("--chunk", type=int, default=0)
+ap.add_argument("--bps", type=int, default=0)
+a = ap.parse_args()
+v = case(a.case, a.scale)
+plan = mdz_b200.Plan(v, 0)
+plan.tune(a.chunk, a.bps)
+for i in range(a.reps):
+    t0 = time.perf_counter()
+    plan.launch()
+    plan.wait()
+    dt = time.perf_counter() - t0
+    raw = plan.fetch()
+    it = int(np.where(raw > 0, raw, v.depth).astype(np.int64).sum())
+    print("%s rep %d: %.2f ms, %d iterations, %.3f G it/s, kernel %s" % (a.case, i, dt * 1e3, it, it / dt / 1e9, plan.kernel_info()))
