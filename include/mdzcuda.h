@@ -87,8 +87,9 @@ int mdzcuda_device_count(void);
 mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* view, int device,
                                   int band_first, int band_stride);
 
-/* Tunables (before launch): iterations between queue refills (0 = default),
- * resident blocks per SM (0 = occupancy maximum). */
+/* Tunables (before launch): iterations between queue refills (0 = default; a
+ * negative value -n means n with the speculative iteration body switched off,
+ * for A/B measurements), resident blocks per SM (0 = occupancy maximum). */
 int mdzcuda_plan_tune(mdzcuda_plan*, int chunk_iters, int blocks_per_sm);
 
 /* Enqueue the reset + escape-time kernel on `cuda_stream` (a cudaStream_t; NULL

@@ -48,6 +48,7 @@ struct EscapeParams {
     int family;
     int fractal;
     int chunk;              // iterations between refills
+    int spec;               // 1: try the speculative branch-free iteration first
 };
 
 constexpr int kBlock = 128;
@@ -60,6 +61,10 @@ __device__ __forceinline__ void load_entry(const CoordTable& t, int i, Num<N>& v
     v.e = __ldg(&t.e[i]);
     v.s = __ldg(&t.s[i]);
 }
+
+// limb counts for which the speculative iteration (escape_step.cuh) is compiled in:
+// it keeps the previous state alive for the fall-back, 4N extra registers
+template <int N> struct SpecLimbs { static constexpr bool value = N >= 3 && N <= 10; };
 
 // resident blocks per SM the register allocator is asked to make room for
 template <int N> struct MinBlocks {
@@ -89,6 +94,8 @@ escape_mpfr_kernel(const EscapeParams p)
 
     bool active = false;
     bool exhausted = false;         // warp-uniform
+    bool use_spec = SpecLimbs<N>::value && p.spec != 0;     // warp-uniform
+    int spec_pause = 0, spec_backoff = 8;
     unsigned pix = 0;
 
     const bool abs_im = p.fractal == FRACTAL_BURNING_SHIP;
@@ -132,9 +139,14 @@ escape_mpfr_kernel(const EscapeParams p)
         if (!__any_sync(0xffffffffu, active)) break;
 
         // ---- iterate ------------------------------------------------------
+        uint32_t rare_seen = 0;
         for (int k = 0; k < p.chunk; ++k) {
             if (active) {
-                const bool esc = pixel_step<N>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re);
+                bool esc;
+                if (SpecLimbs<N>::value)
+                    esc = pixel_step_auto<N>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re, use_spec, rare_seen);
+                else
+                    esc = pixel_step<N>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re);
                 const int iter = st.iter;
                 if (esc || iter >= p.depth) {
                     p.raw[pix] = esc ? iter : 0;
@@ -150,6 +162,20 @@ escape_mpfr_kernel(const EscapeParams p)
                 }
             }
             if (!__any_sync(0xffffffffu, active)) break;
+        }
+        // ---- adapt: speculation is only worth it while fall-backs are scarce ----
+        if (SpecLimbs<N>::value) {
+            if (use_spec) {
+                // a lane that fell back in at least a quarter of the chunk votes against
+                const unsigned against = __popc(__ballot_sync(0xffffffffu, rare_seen * 4u >= (unsigned)p.chunk));
+                if (against * 4u >= 32u) {      // back off exponentially: 16, 32, ... 4096 chunks
+                    use_spec = false;
+                    spec_backoff = spec_backoff < 4096 ? spec_backoff * 2 : 4096;
+                    spec_pause = spec_backoff;
+                } else if (against == 0) spec_backoff = 8;
+            } else if (--spec_pause <= 0) {
+                use_spec = p.spec != 0;
+            }
         }
     }
 }

@@ -77,4 +77,62 @@ MDZ_HD bool pixel_step(PixelState<N>& st, const uint32_t* cre_m, const uint32_t*
     return esc;
 }
 
+
+// Speculative iteration: the same arithmetic built from the branch-free
+// *_spec operations (mpfr_sf.cuh), i.e. one basic block in which ptxas overlaps
+// the IMAD.WIDE chains of the products with the shift/add chains of the sums.
+// Any condition the branch-free code does not cover raises `rare`; the caller
+// then restores the previous state and runs pixel_step (below in
+// pixel_step_auto).  The escape sum is not part of the speculation: when
+// max(e) is 2 or 3 it is computed afterwards with the general fadd.
+template <int N>
+MDZ_HD bool pixel_step_spec(PixelState<N>& st, const uint32_t* cre_m, const uint32_t* cim_m,
+                            uint32_t* scr, const RoundCfg& rc, bool abs_im, int abs_re, uint32_t& rare)
+{
+    ++st.iter;
+    Num<N> t, u, c, c2;
+    MDZ_UNROLL
+    for (int q = 0; q < N; ++q) c.m[q] = cim_m[q * kScratchStride];
+    c.e = st.cim_e; c.s = st.cim_s;
+    MDZ_UNROLL
+    for (int q = 0; q < N; ++q) c2.m[q] = cre_m[q * kScratchStride];
+    c2.e = st.cre_e; c2.s = st.cre_s;
+    fmul_spec<N>(st.wre, st.wim, t, rc, rare);
+    fadd_spec<N, MODE_SUB_POS>(st.wre2, st.wim2, u, rc, rare);
+    if (abs_re == 1 || (abs_re == 2 && (st.iter & 1))) u.s = 0;
+    fadd_spec<N, MODE_GENERIC>(u, c2, st.wre, rc, rare);
+    if (t.m[N - 1] != 0) t.e += 1;
+    if (abs_im) t.s = 0;
+    fadd_spec<N, MODE_GENERIC>(t, c, st.wim, rc, rare);
+    fsqr_spec<N>(st.wre, st.wre2, rc, rare);
+    fsqr_spec<N>(st.wim, st.wim2, rc, rare);
+    const int32_t emax = st.wim2.e > st.wre2.e ? st.wim2.e : st.wre2.e;
+    bool esc = emax >= 4;
+    if (rare == 0 && !esc && emax >= 2) {
+        MDZ_COUNT(CNT_ESC_ADD);
+        fadd<N, MODE_ADD_POS>(st.wim2, st.wre2, t, rc, scr);
+        esc = greater_than_4<N>(t);
+    }
+    return esc;
+}
+
+// Speculate when the warp's recent history says it pays (use_spec is
+// warp-uniform and maintained by the kernel), fall back per lane otherwise.
+template <int N>
+MDZ_HD bool pixel_step_auto(PixelState<N>& st, const uint32_t* cre_m, const uint32_t* cim_m,
+                            uint32_t* scr, const RoundCfg& rc, bool abs_im, int abs_re,
+                            bool use_spec, uint32_t& rare_seen)
+{
+    if (use_spec) {
+        const PixelState<N> keep = st;
+        uint32_t rare = 0;
+        const bool esc = pixel_step_spec<N>(st, cre_m, cim_m, scr, rc, abs_im, abs_re, rare);
+        if (rare == 0) return esc;
+        MDZ_COUNT(CNT_SPEC_FALLBACK);
+        rare_seen += 1;
+        st = keep;
+    }
+    return pixel_step<N>(st, cre_m, cim_m, scr, rc, abs_im, abs_re);
+}
+
 }  // namespace mdz

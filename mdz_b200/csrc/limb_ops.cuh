@@ -27,7 +27,7 @@ namespace mdz {
 // path counters: compiled in for the host emulation only (tests/host_emu)
 #if defined(MDZ_HOST_EMU)
 enum { CNT_ADD_FAST, CNT_ADD_MEDIUM, CNT_ADD_COPY, CNT_ADD_TIE, CNT_ADD_CANCEL, CNT_ROUND_CARRY,
-       CNT_MUL_BAIL, CNT_ESC_ADD, CNT_ITER, CNT_N };
+       CNT_MUL_BAIL, CNT_ESC_ADD, CNT_ITER, CNT_SPEC_FALLBACK, CNT_SPEC_GAP, CNT_SPEC_TIE, CNT_SPEC_CANCEL, CNT_SPEC_ROUND, CNT_SPEC_MUL, CNT_N };
 static thread_local unsigned long long g_counts[CNT_N];
 #define MDZ_COUNT(id) (++::mdz::g_counts[::mdz::id])
 #else

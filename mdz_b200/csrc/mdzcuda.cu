@@ -127,7 +127,7 @@ struct mdzcuda_plan {
     unsigned char* d_band_flag = nullptr;
     cudaStream_t side = nullptr;        // progress / cancel traffic while the kernel runs
     cudaEvent_t done_ev = nullptr;
-    int chunk = 0, blocks_per_sm = 0;
+    int chunk = 0, blocks_per_sm = 0, spec = 1;
     mdzcuda_kernel_info info;
     unsigned int* h_pinned = nullptr;   // 4 words of pinned staging
 };
@@ -304,7 +304,8 @@ fail:
 extern "C" int mdzcuda_plan_tune(mdzcuda_plan* pl, int chunk_iters, int blocks_per_sm)
 {
     if (!pl) return 0;
-    pl->chunk = chunk_iters > 0 ? chunk_iters : 0;
+    pl->spec = chunk_iters < 0 ? 0 : 1;      // negative chunk: speculative body off (A/B measurements)
+    pl->chunk = chunk_iters < 0 ? -chunk_iters : chunk_iters;
     pl->blocks_per_sm = blocks_per_sm > 0 ? blocks_per_sm : 0;
     return 1;
 }
@@ -343,6 +344,7 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         p.family = pl->view.family;
         p.fractal = pl->view.fractal;
         p.chunk = pl->chunk ? pl->chunk : default_chunk(pl->n32);
+        p.spec = pl->spec;
         int bps = pl->blocks_per_sm ? pl->blocks_per_sm : pl->info.blocks_per_sm;
         if (bps > pl->info.blocks_per_sm) bps = pl->info.blocks_per_sm;
         long long npx = (long long)pl->local_lines * pl->view.real_width;

@@ -388,6 +388,78 @@ MDZ_HD void fadd(const Num<N>& a, const Num<N>& b, Num<N>& r, const RoundCfg& rc
     if (carry) { MDZ_COUNT(CNT_ROUND_CARRY); r = round_carry_general<N>(r); }   // rare: increment leaves limb 0
 }
 
+
+// ---------------------------------------------------------------------------
+// Speculative, branch-free versions: no rare-case handling at all, only a flag.
+// A whole iteration built from these is one basic block, so ptxas can overlap
+// the IMAD.WIDE chains of a product with the shift/add chains of an independent
+// sum.  When `rare` comes back non-zero the caller discards the results.
+// ---------------------------------------------------------------------------
+template <int N, int MODE>
+MDZ_HD void fadd_spec(const Num<N>& a, const Num<N>& b, Num<N>& r, const RoundCfg& rc, uint32_t& rare)
+{
+    const uint32_t sb = (MODE == MODE_SUB_POS) ? 1u : (MODE == MODE_ADD_POS ? 0u : b.s);
+    const uint32_t sa = (MODE == MODE_GENERIC) ? a.s : 0u;
+    const bool sub = (MODE == MODE_SUB_POS) ? true : (MODE == MODE_ADD_POS ? false : (sa != sb));
+    const int32_t d = a.e - b.e;
+    const uint32_t ad = (uint32_t)(d < 0 ? -d : d);
+    rare |= (ad >= 31u) ? 1u : 0u;
+    if (ad >= 31u) MDZ_COUNT(CNT_SPEC_GAP);
+    const uint32_t sha = 1u + (d < 0 ? ad : 0u);
+    const uint32_t shb = 1u + (d > 0 ? ad : 0u);
+    uint32_t xa[N + 1], xb[N + 1];
+    xa[0] = fsr(0u, a.m[0], sha); xb[0] = fsr(0u, b.m[0], shb);
+    MDZ_UNROLL
+    for (int i = 1; i < N; ++i) { xa[i] = fsr(a.m[i - 1], a.m[i], sha); xb[i] = fsr(b.m[i - 1], b.m[i], shb); }
+    xa[N] = a.m[N - 1] >> sha; xb[N] = b.m[N - 1] >> shb;
+    uint32_t x[N + 1];
+    uint32_t s = sa;
+    if (MODE == MODE_ADD_POS) {
+        x[0] = add_cc(xa[0], xb[0]);
+        MDZ_UNROLL
+        for (int i = 1; i < N; ++i) x[i] = addc_cc(xa[i], xb[i]);
+        x[N] = addc(xa[N], xb[N]);
+    } else {
+        const bool a_big = d > 0 || (d == 0 && a.m[N - 1] > b.m[N - 1]);
+        rare |= (sub && d == 0 && a.m[N - 1] == b.m[N - 1]) ? 1u : 0u;
+        if (sub && d == 0 && a.m[N - 1] == b.m[N - 1]) MDZ_COUNT(CNT_SPEC_TIE);
+        const uint32_t ma = (sub && !a_big) ? 0xffffffffu : 0u;
+        const uint32_t mb = (sub && a_big) ? 0xffffffffu : 0u;
+        s = (sub && !a_big) ? sb : sa;
+        (void)add_cc(sub ? 1u : 0u, 0xffffffffu);
+        MDZ_UNROLL
+        for (int i = 0; i < N; ++i) x[i] = addc_cc(xa[i] ^ ma, xb[i] ^ mb);
+        x[N] = addc(xa[N] ^ ma, xb[N] ^ mb);
+        rare |= (x[N] == 0) ? 1u : 0u;
+        if (x[N] == 0) MDZ_COUNT(CNT_SPEC_CANCEL);
+    }
+    const uint32_t lz = (uint32_t)clz32(x[N]);
+    MDZ_UNROLL
+    for (int i = N; i >= 1; --i) x[i] = fsl(x[i - 1], x[i], lz);
+    x[0] <<= lz;
+    rare |= round_rn_fast<N>(x, 0u, rc) ? 1u : 0u;
+    MDZ_UNROLL
+    for (int i = 0; i < N; ++i) r.m[i] = x[i + 1];
+    r.e = (d < 0 ? b.e : a.e) + 1 - (int32_t)lz;
+    r.s = s;
+}
+
+template <int N>
+MDZ_HD void fmul_spec(const Num<N>& a, const Num<N>& b, Num<N>& r, const RoundCfg& rc, uint32_t& rare)
+{
+    uint32_t t[N + 2];
+    mul_hi<N>(a.m, b.m, t);
+    rare |= finish_high<N>(t, a.e + b.e, a.s ^ b.s, r, rc) ? 1u : 0u;
+}
+
+template <int N>
+MDZ_HD void fsqr_spec(const Num<N>& a, Num<N>& r, const RoundCfg& rc, uint32_t& rare)
+{
+    uint32_t t[N + 2];
+    sqr_hi<N>(a.m, t);
+    rare |= finish_high<N>(t, a.e + a.e, 0u, r, rc) ? 1u : 0u;
+}
+
 // a > 4 ?   (4 = 0.1b * 2^3)
 template <int N>
 MDZ_HD bool greater_than_4(const Num<N>& a)

@@ -55,7 +55,7 @@ extern "C" int emu_binop(int op, long prec,
 
 // ---- whole-pixel emulation: the kernel's pixel_init / pixel_step on the host ----
 template <int N>
-static long pixel(long prec, int fractal, long depth,
+static long pixel(long prec, int fractal, long depth, int spec,
                   const uint64_t* const* l, const int* sg, const long* ex)
 {
     RoundCfg rc = make_round_cfg(N, (int)prec);
@@ -69,13 +69,14 @@ static long pixel(long prec, int fractal, long depth,
     pixel_init<N>(st, v[0], v[1], v[2], v[3], rc, cre, cim);
     const bool abs_im = fractal == FRACTAL_BURNING_SHIP;
     const int abs_re = fractal == FRACTAL_GENERALIZED_CELTIC ? 1 : fractal == FRACTAL_VARIANT ? 2 : 0;
+    uint32_t rare_seen = 0;
     while (st.iter < depth)
-        if (pixel_step<N>(st, cre, cim, scr, rc, abs_im, abs_re)) return st.iter;
+        if (pixel_step_auto<N>(st, cre, cim, scr, rc, abs_im, abs_re, spec != 0, rare_seen)) return st.iter;
     return 0;
 }
 
-#define PCASE(n) case n: return pixel<n>(prec, fractal, depth, l, sg, ex);
-extern "C" long emu_pixel(long prec, int fractal, long depth,
+#define PCASE(n) case n: return pixel<n>(prec, fractal, depth, spec, l, sg, ex);
+extern "C" long emu_pixel(long prec, int fractal, long depth, int spec,
                           const uint64_t* xl, int xs, long xe, const uint64_t* yl, int ys, long ye,
                           const uint64_t* cxl, int cxs, long cxe, const uint64_t* cyl, int cys, long cye)
 {
