@@ -139,11 +139,16 @@ int mdzcuda_render(const mdzcuda_view* view, int32_t* raw_host,
                    int ndev, const int* devices);
 
 /*
- * Measured integer-multiply peak of a device: runs a register-only
- * IMAD.WIDE.U32 microbenchmark for about `ms` milliseconds and returns 32x32->64
- * multiply-accumulates per second (the roofline denominator of SURVEY 8(d)).
+ * Measured integer-multiply peaks of a device (register-only microbenchmarks,
+ * about `ms` milliseconds each), in operations per second:
+ *   mdzcuda_imad_peak    32x32->64 multiply-accumulates issued as IMAD.WIDE.U32.X
+ *                        carry chains, the unit SURVEY 8(d) counts (W(N) = 2N^2+N);
+ *   mdzcuda_imad32_peak  independent 32-bit IMAD (low half), the pipe's nominal
+ *                        "64 IMAD/clk/SM" issue rate.
+ * On B200 the 64-bit form runs at half the rate of the 32-bit one.
  */
 double mdzcuda_imad_peak(int device, int ms);
+double mdzcuda_imad32_peak(int device, int ms);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,7 @@ SYMBOLS = {
     "mdzcuda_plan_destroy": (None, [C.c_void_p]),
     "mdzcuda_render": (C.c_int, [C.POINTER(View), C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "mdzcuda_imad_peak": (C.c_double, [C.c_int, C.c_int]),
+    "mdzcuda_imad32_peak": (C.c_double, [C.c_int, C.c_int]),
 }
 
 

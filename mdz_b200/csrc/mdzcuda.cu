@@ -454,29 +454,47 @@ extern "C" int mdzcuda_render(const mdzcuda_view* view, int32_t* raw_host, int n
 }
 
 // ---------------------------------------------------------------------------
-// IMAD.WIDE.U32 peak microbenchmark (register-only, 8 independent chains/thread)
+// Integer-multiply peak microbenchmarks (register-only).
+//
+//  wide:  IMAD.WIDE.U32(.X) carry chains exactly as mul_full / mul_hi emit them
+//         (two interleaved chains of four 32x32->64 multiply-accumulates) -- the
+//         instruction that performs the unit SURVEY 8(d) counts.
+//  lo32:  independent 32-bit IMAD (low half only), the pipe's nominal issue
+//         rate that SURVEY 8(d) quotes as "64 IMAD/clk/SM".
+// The multiplier operand is data dependent so ptxas cannot hoist the product
+// (it does, and turns a naive loop into plain 64-bit adds).
+// On B200 the first runs at half the rate of the second (profiles/r1_pipe_microbench.txt).
 // ---------------------------------------------------------------------------
+template <int WIDE>
 __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t seed, int iters, unsigned long long* out)
 {
     uint32_t a = seed + threadIdx.x, b = seed * 2654435761u + blockIdx.x;
-    unsigned long long acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = (unsigned long long)(a + i) << 7;
+    uint32_t r0 = a, r1 = b, r2 = a ^ b, r3 = a + b, r4 = a * 3, r5 = b * 5, r6 = a * 7, r7 = b * 9;
+    uint32_t r8 = a + 1, r9 = b + 2, r10 = a + 3, r11 = b + 4, r12 = a + 5, r13 = b + 6, r14 = a + 7, r15 = b + 8;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a), "r"(b));
+            if (WIDE) {
+                asm volatile(
+                    "mad.lo.cc.u32 %0,%16,%17,%0; madc.hi.cc.u32 %1,%16,%17,%1; madc.lo.cc.u32 %2,%16,%17,%2; madc.hi.cc.u32 %3,%16,%17,%3;"
+                    "madc.lo.cc.u32 %4,%16,%17,%4; madc.hi.cc.u32 %5,%16,%17,%5; madc.lo.cc.u32 %6,%16,%17,%6; madc.hi.u32 %7,%16,%17,%7;"
+                    "mad.lo.cc.u32 %8,%16,%17,%8; madc.hi.cc.u32 %9,%16,%17,%9; madc.lo.cc.u32 %10,%16,%17,%10; madc.hi.cc.u32 %11,%16,%17,%11;"
+                    "madc.lo.cc.u32 %12,%16,%17,%12; madc.hi.cc.u32 %13,%16,%17,%13; madc.lo.cc.u32 %14,%16,%17,%14; madc.hi.u32 %15,%16,%17,%15;"
+                    : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7),
+                      "+r"(r8), "+r"(r9), "+r"(r10), "+r"(r11), "+r"(r12), "+r"(r13), "+r"(r14), "+r"(r15) : "r"(a), "r"(b));
+            } else {
+                asm volatile("mad.lo.u32 %0,%1,%8,%0; mad.lo.u32 %1,%2,%8,%1; mad.lo.u32 %2,%3,%8,%2; mad.lo.u32 %3,%4,%8,%3;"
+                             "mad.lo.u32 %4,%5,%8,%4; mad.lo.u32 %5,%6,%8,%5; mad.lo.u32 %6,%7,%8,%6; mad.lo.u32 %7,%0,%8,%7;"
+                    : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7) : "r"(b));
+            }
         }
     }
-    unsigned long long x = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x ^= acc[i];
-    if (x == 0x1234567ull) out[0] = x;      // keep the chains alive
+    uint32_t x = r0 ^ r1 ^ r2 ^ r3 ^ r4 ^ r5 ^ r6 ^ r7 ^ r8 ^ r9 ^ r10 ^ r11 ^ r12 ^ r13 ^ r14 ^ r15;
+    if (x == 0x1234567u) out[0] = x;      // keep the chains alive
 }
 
-extern "C" double mdzcuda_imad_peak(int device, int ms)
+template <int WIDE>
+static double run_imad_peak(int device, int ms)
 {
     g_err.clear();
     if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice failed"); return 0.0; }
@@ -488,17 +506,17 @@ extern "C" double mdzcuda_imad_peak(int device, int ms)
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     int iters = 2000;
-    double best = 0.0;
-    double spent = 0.0;
-    imad_peak_kernel<<<blocks, threads>>>(1u, 200, d_out);        // warm-up
+    double best = 0.0, spent = 0.0;
+    imad_peak_kernel<WIDE><<<blocks, threads>>>(1u, 200, d_out);        // warm-up
     cudaDeviceSynchronize();
     for (int rep = 0; rep < 64 && spent < (double)ms; ++rep) {
         cudaEventRecord(e0);
-        imad_peak_kernel<<<blocks, threads>>>(rep + 2u, iters, d_out);
+        imad_peak_kernel<WIDE><<<blocks, threads>>>(rep + 2u, iters, d_out);
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) { set_err("imad kernel failed"); best = 0.0; break; }
         float t = 0; cudaEventElapsedTime(&t, e0, e1);
         spent += t;
+        // multiply-accumulates per thread per iteration: 8 x (8 wide) or 8 x (8 lo)
         const double macs = (double)blocks * threads * (double)iters * 64.0;
         const double rate = macs / (t * 1e-3);
         if (rate > best) best = rate;
@@ -508,3 +526,6 @@ extern "C" double mdzcuda_imad_peak(int device, int ms)
     cudaFree(d_out);
     return best;
 }
+
+extern "C" double mdzcuda_imad_peak(int device, int ms) { return run_imad_peak<1>(device, ms); }
+extern "C" double mdzcuda_imad32_peak(int device, int ms) { return run_imad_peak<0>(device, ms); }

@@ -81,8 +81,11 @@ def device_count():
     return _l.lib.mdzcuda_device_count()
 
 
-def imad_peak(device=0, ms=200):
-    r = _l.lib.mdzcuda_imad_peak(device, ms)
+def imad_peak(device=0, ms=200, wide=True):
+    """Measured multiply peak, ops/s: wide=True is IMAD.WIDE.U32.X carry chains
+    (32x32->64 MACs, the roofline unit), wide=False the 32-bit IMAD issue rate."""
+    fn = _l.lib.mdzcuda_imad_peak if wide else _l.lib.mdzcuda_imad32_peak
+    r = fn(device, ms)
     if r <= 0:
         raise _l.MdzCudaError("imad_peak: " + _l.last_error())
     return r
