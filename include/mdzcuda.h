@@ -106,6 +106,14 @@ int mdzcuda_plan_cancel(mdzcuda_plan*);
 int mdzcuda_plan_bands_done(mdzcuda_plan*);
 int mdzcuda_plan_bands_total(mdzcuda_plan*);
 
+/* Progressive delivery while a launch is running (what rth_process_lines_rendered
+ * is fed from): copy the per-band completion flags (bands_total bytes, 1 = all
+ * aa_factor*real_width supersamples of that band are final) and return how many
+ * are set; copy `count` local bands starting at `first_local_band` into their
+ * place in a full-size host raw_data array. */
+int mdzcuda_plan_poll_bands(mdzcuda_plan*, unsigned char* flags_host);
+int mdzcuda_plan_fetch_bands(mdzcuda_plan*, int32_t* raw_host, int first_local_band, int count);
+
 /* Copy this plan's lines into a full-size host raw_data array
  * (real_width*real_height int32, img->raw_data layout: line*real_width+ix). */
 int mdzcuda_plan_fetch(mdzcuda_plan*, int32_t* raw_host);

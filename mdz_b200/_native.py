@@ -49,6 +49,8 @@ SYMBOLS = {
     "mdzcuda_plan_bands_done": (C.c_int, [C.c_void_p]),
     "mdzcuda_plan_bands_total": (C.c_int, [C.c_void_p]),
     "mdzcuda_plan_fetch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mdzcuda_plan_poll_bands": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mdzcuda_plan_fetch_bands": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mdzcuda_plan_device_raw": (C.c_void_p, [C.c_void_p]),
     "mdzcuda_plan_local_lines": (C.c_int, [C.c_void_p]),
     "mdzcuda_plan_kernel_info": (C.c_int, [C.c_void_p, C.POINTER(KernelInfo)]),

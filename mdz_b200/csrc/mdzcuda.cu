@@ -407,6 +407,35 @@ extern "C" int mdzcuda_plan_fetch(mdzcuda_plan* pl, int32_t* raw_host)
     return 1;
 }
 
+
+extern "C" int mdzcuda_plan_poll_bands(mdzcuda_plan* pl, unsigned char* flags_host)
+{
+    if (!pl || !flags_host) { set_err("null argument"); return -1; }
+    if (cudaSetDevice(pl->device) != cudaSuccess) return -1;
+    if (pl->nbands == 0) return 0;
+    if (cudaMemcpyAsync(flags_host, pl->d_band_flag, pl->nbands, cudaMemcpyDeviceToHost, pl->side) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(pl->side) != cudaSuccess) return -1;
+    int done = 0;
+    for (int i = 0; i < pl->nbands; ++i) done += flags_host[i] != 0;
+    return done;
+}
+
+extern "C" int mdzcuda_plan_fetch_bands(mdzcuda_plan* pl, int32_t* raw_host, int first_local_band, int count)
+{
+    if (!pl || !raw_host) { set_err("null argument"); return 0; }
+    if (first_local_band < 0 || count < 0 || first_local_band + count > pl->nbands) { set_err("band range"); return 0; }
+    if (count == 0) return 1;
+    CUDA_OK(cudaSetDevice(pl->device));
+    const int W = pl->view.real_width, aa = pl->view.aa_factor;
+    const size_t band_bytes = (size_t)aa * W * sizeof(int32_t);
+    const int gband = pl->band_first + first_local_band * pl->band_stride;
+    CUDA_OK(cudaMemcpy2DAsync(raw_host + (size_t)gband * aa * W, band_bytes * pl->band_stride,
+                              pl->d_raw + (size_t)first_local_band * aa * W, band_bytes, band_bytes, count,
+                              cudaMemcpyDeviceToHost, pl->side));
+    CUDA_OK(cudaStreamSynchronize(pl->side));
+    return 1;
+}
+
 extern "C" void* mdzcuda_plan_device_raw(mdzcuda_plan* pl) { return pl ? pl->d_raw : nullptr; }
 extern "C" int mdzcuda_plan_local_lines(mdzcuda_plan* pl) { return pl ? pl->local_lines : -1; }
 
