@@ -152,6 +152,7 @@ def side_precisions(torch, device):
         ("mpfr512", make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", 960, 540, precision=512, depth=10000)),
     ]
     peak = mdz_b200.imad_peak(device, 100)
+    peak32 = mdz_b200.imad_peak(device, 100, wide=False)
     for name, view in cases:
         plan = mdz_b200.Plan(view, device)
         st = torch.cuda.current_stream().cuda_stream
@@ -166,7 +167,8 @@ def side_precisions(torch, device):
                      "view": "%dx%d" % (view.real_width, view.real_height),
                      "limbs": ki["limbs"], "regs": ki["regs_per_thread"], "spill_bytes": ki["local_bytes"],
                      "blocks_per_sm": ki["blocks_per_sm"],
-                     "imad_frac": rate * macs_per_iteration(ki["limbs"]) / peak}
+                     "imad_frac": rate * macs_per_iteration(ki["limbs"]) / peak,
+                     "frac_of_imad32_issue": rate * macs_per_iteration(ki["limbs"]) / peak32}
         plan.close()
     return out
 
@@ -263,7 +265,8 @@ def main():
 
     if rank == 0:
         ki = plan.kernel_info()
-        peak = mdz_b200.imad_peak(local, 200)
+        peak = mdz_b200.imad_peak(local, 200)                  # IMAD.WIDE.U32.X chains: 32x32->64 MAC/s
+        peak32 = mdz_b200.imad_peak(local, 200, wide=False)    # 32-bit IMAD issue rate
         macs = macs_per_iteration(ki["limbs"])
         kernel_rate = (total_iters / world) / (kernel_ms * 1e-3)        # this GPU's kernel alone
         line = {
@@ -285,9 +288,14 @@ def main():
             "roofline": {"bound": "imad", "achieved": kernel_rate * macs / 1e12, "peak": peak / 1e12,
                          "unit": "T 32x32->64 MAC/s", "frac": kernel_rate * macs / peak,
                          "traffic": None,
-                         "note": "achieved = it/s x W(N)=2N^2+N MACs (N=%d limbs -> %d); peak = IMAD.WIDE.U32 "
-                                 "microbenchmark measured in this run (MEASURED_PEAKS.json has no integer peak); "
-                                 "kernel avg launch %.3f ms by CUDA events" % (ki["limbs"], macs, kernel_ms)},
+                         "peak_imad32": peak32 / 1e12,
+                         "frac_of_imad32_issue": kernel_rate * macs / peak32,
+                         "note": "integer-pipe roofline (SURVEY 8d), not hbm/tensor. achieved = it/s x W(N)=2N^2+N "
+                                 "full-schoolbook MACs (N=%d limbs -> %d; the kernel forms only the high ~59%% of each "
+                                 "product, DESIGN.md 2.1); peak = IMAD.WIDE.U32.X carry-chain microbenchmark measured in "
+                                 "this run (MEASURED_PEAKS.json has no integer peak); peak_imad32 = 32-bit IMAD issue rate, "
+                                 "twice that; kernel avg launch %.3f ms by CUDA events; HBM traffic is 4 B per pixel out"
+                                 % (ki["limbs"], macs, kernel_ms)},
             "kernel": ki,
         }
         # CPU baseline: the unmodified reference pool on this box's cores, bounded sample
