@@ -16,6 +16,7 @@
 // warp-aggregated atomicAdd.
 #pragma once
 #include "escape_step.cuh"
+#include "mpf_sf.cuh"
 
 namespace mdz {
 
@@ -176,6 +177,93 @@ escape_mpfr_kernel(const EscapeParams p)
             } else if (--spec_pause <= 0) {
                 use_spec = p.spec != 0;
             }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------
+// GMP mpf mode (reference src/fractal.c:260-397 + frac_*_gmp): same persistent
+// scheduler, arithmetic from mpf_sf.cuh.  Tables hold NL 64-bit limbs per entry
+// as 2*NL 32-bit words (low word first), the limb exponent, the sign.
+// ---------------------------------------------------------------------------
+template <int NL>
+__device__ __forceinline__ void load_mpf_entry(const CoordTable& t, int i, Mpf<NL>& v)
+{
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+        const uint32_t lo = __ldg(&t.m[(size_t)(2 * k) * t.count + i]);
+        const uint32_t hi = __ldg(&t.m[(size_t)(2 * k + 1) * t.count + i]);
+        v.l[k] = ((uint64_t)hi << 32) | lo;
+    }
+    v.e = __ldg(&t.e[i]);
+    v.s = __ldg(&t.s[i]);
+}
+
+template <int NL>
+__global__ void __launch_bounds__(kBlock)
+escape_gmp_kernel(const EscapeParams p)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned total = (unsigned)p.width * (unsigned)p.lines;
+    GmpPixel<NL> st;
+    st.iter = 0;
+    bool active = false;
+    bool exhausted = false;
+    unsigned pix = 0;
+    const bool abs_im = p.fractal == FRACTAL_BURNING_SHIP;
+    const int  abs_re = p.fractal == FRACTAL_GENERALIZED_CELTIC ? 1
+                      : p.fractal == FRACTAL_VARIANT ? 2 : 0;
+    for (;;) {
+        {
+            int stop = 0;
+            if (lane == 0) stop = *p.cancel;
+            if (__shfl_sync(0xffffffffu, stop, 0)) break;
+        }
+        if (!exhausted) {
+            const unsigned need = __ballot_sync(0xffffffffu, !active);
+            if (need) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(p.queue, (unsigned)__popc(need));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base + (unsigned)__popc(need) >= total) exhausted = true;
+                if (!active) {
+                    const unsigned idx = base + (unsigned)__popc(need & ((1u << lane) - 1u));
+                    if (idx < total) {
+                        pix = idx;
+                        const int line = (int)(idx / (unsigned)p.width);
+                        const int ix = (int)(idx - (unsigned)line * (unsigned)p.width);
+                        Mpf<NL> x, y, cx, cy;
+                        load_mpf_entry<NL>(p.xs, ix, x);
+                        load_mpf_entry<NL>(p.ys, line, y);
+                        if (p.family == FAMILY_JULIA) {
+                            load_mpf_entry<NL>(p.jc, 0, cx);
+                            load_mpf_entry<NL>(p.jc, 1, cy);
+                        } else { cx = x; cy = y; }
+                        gmp_pixel_init<NL>(st, x, y, cx, cy);
+                        active = true;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+        for (int k = 0; k < p.chunk; ++k) {
+            if (active) {
+                const bool esc = gmp_pixel_step<NL>(st, abs_im, abs_re);
+                if (esc || st.iter >= p.depth) {
+                    p.raw[pix] = esc ? st.iter : 0;
+                    __threadfence();
+                    active = false;
+                    const unsigned band = (pix / (unsigned)p.width) / (unsigned)p.aa;
+                    const unsigned done = atomicAdd(&p.band_count[band], 1u) + 1u;
+                    if (done == (unsigned)p.width * (unsigned)p.aa) {
+                        __threadfence();
+                        p.band_flag[band] = 1;
+                        atomicAdd((unsigned int*)p.bands_done, 1u);
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, active)) break;
         }
     }
 }

@@ -73,6 +73,26 @@ struct HostTable {
         e[i] = (int32_t)ex;
         s[i] = v->_mpfr_sign < 0 ? 1u : 0u;
     }
+    // from an mpf_t: |size| limbs top-aligned into nl64 = n32/2 limbs, zero padded below
+    void set_mpf(int i, const __mpf_struct* v)
+    {
+        const int nl = n32 / 2;
+        int size = v->_mp_size < 0 ? -v->_mp_size : v->_mp_size;
+        set_zero_entry(i);
+        e[i] = 0;
+        if (size == 0) return;
+        const mp_limb_t* d = v->_mp_d;
+        int skip = 0;
+        if (size > nl) { skip = size - nl; size = nl; }     // cannot happen for values of this precision
+        for (int k = 0; k < size; ++k) {
+            const uint64_t w = d[skip + k];
+            const int at = nl - size + k;
+            m[(size_t)(2 * at) * count + i] = (uint32_t)w;
+            m[(size_t)(2 * at + 1) * count + i] = (uint32_t)(w >> 32);
+        }
+        e[i] = (int32_t)v->_mp_exp;
+        s[i] = v->_mp_size < 0 ? 1u : 0u;
+    }
     // from an x87 long double: 64-bit significand, same value as MPFR p=64
     void set_ld(int i, long double v)
     {
@@ -128,6 +148,7 @@ struct mdzcuda_plan {
     cudaStream_t side = nullptr;        // progress / cancel traffic while the kernel runs
     cudaEvent_t done_ev = nullptr;
     int chunk = 0, blocks_per_sm = 0, spec = 1;
+    bool gmp = false;
     mdzcuda_kernel_info info;
     unsigned int* h_pinned = nullptr;   // 4 words of pinned staging
 };
@@ -135,6 +156,18 @@ struct mdzcuda_plan {
 typedef void (*kernel_fn)(const EscapeParams);
 
 template <int N> static kernel_fn kfn() { return escape_mpfr_kernel<N>; }
+
+template <int NL> static kernel_fn gfn() { return escape_gmp_kernel<NL>; }
+
+// GMP mode: nl = P+1 64-bit limbs, P = mpf_init2's precision in limbs
+static kernel_fn gmp_kernel_for_limbs(int nl)
+{
+    switch (nl) {
+    case 3: return gfn<3>();  case 4: return gfn<4>();  case 5: return gfn<5>();  case 6: return gfn<6>();
+    case 7: return gfn<7>();  case 8: return gfn<8>();  case 9: return gfn<9>();  case 10: return gfn<10>();
+    default: return nullptr;
+    }
+}
 
 static kernel_fn kernel_for_limbs(int n)
 {
@@ -183,6 +216,50 @@ static int prologue_mpfr(const mdzcuda_view* v, const std::vector<int>& lines,
     }
     mpfr_clear(img_rw); mpfr_clear(img_xmin); mpfr_clear(width);
     mpfr_clear(t1); mpfr_clear(x); mpfr_clear(y);
+    return 1;
+}
+
+// ---- prologue: GMP mpf mode (reference src/fractal.c:283-328, :341-342) -------
+static int prologue_gmp(const mdzcuda_view* v, const std::vector<int>& lines,
+                        HostTable& xs, HostTable& ys, HostTable& jc, int n32)
+{
+    if (!v->gxmin || !v->gymax || !v->gwidth) { set_err("GMP mode needs gxmin/gymax/gwidth"); return 0; }
+    const unsigned long p = (unsigned long)v->precision;
+    mpf_t img_rw, img_xmin, width, t1, x, y;
+    mpf_init2(img_rw, p); mpf_init2(img_xmin, p); mpf_init2(width, p);
+    mpf_init2(t1, p); mpf_init2(x, p); mpf_init2(y, p);
+    mpf_set_si(img_rw, v->real_width);                      // fractal.c:300
+    mpf_set(img_xmin, v->gxmin);                            // :301
+    mpf_set(width, v->gwidth);                              // :302
+    xs.init(n32, v->real_width);
+    for (int ix = 0; ix < v->real_width; ++ix) {
+        mpf_ui_div(t1, (unsigned long)ix, img_rw);          // :323
+        mpf_mul(x, t1, width);                              // :325
+        mpf_add(x, x, img_xmin);                            // :326
+        xs.set_mpf(ix, x);
+    }
+    ys.init(n32, (int)lines.size());
+    for (size_t i = 0; i < lines.size(); ++i) {
+        mpf_div(t1, width, img_rw);                         // :307
+        mpf_mul_ui(t1, t1, (unsigned long)lines[i]);        // :309
+        mpf_sub(y, v->gymax, t1);                           // :310
+        ys.set_mpf((int)i, y);
+    }
+    jc.init(n32, 2);
+    if (v->family == MDZCUDA_FAMILY_JULIA) {
+        if (!v->julia_re || !v->julia_im) { set_err("julia family needs julia_re/julia_im"); return 0; }
+        // mpfr_to_gmp (coords.c:13-18): through the decimal text my_mpfr_to_str prints,
+        // i.e. mpfr_snprintf "%.Re" (my_mpfr_to_str.c:68) -- one significant digit with
+        // MPFR >= 4 (SURVEY finding 3); reproduced literally, as the drop-in must
+        char buf[4097];
+        mpfr_snprintf(buf, 4096, "%.Re", v->julia_re);
+        mpf_set_str(x, buf, 10);
+        mpfr_snprintf(buf, 4096, "%.Re", v->julia_im);
+        mpf_set_str(y, buf, 10);
+        jc.set_mpf(0, x); jc.set_mpf(1, y);
+    }
+    mpf_clear(img_rw); mpf_clear(img_xmin); mpf_clear(width);
+    mpf_clear(t1); mpf_clear(x); mpf_clear(y);
     return 1;
 }
 
@@ -241,9 +318,14 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
     else if (v->mode == MDZCUDA_MODE_MPFR) {
         if (v->precision < 33) { set_err("MPFR precision below 33 bits is not supported"); return nullptr; }
         n32 = limbs32_for_prec(v->precision);
-    } else if (v->mode == MDZCUDA_MODE_GMP) { set_err("GMP mpf mode: kernel not built yet"); return nullptr; }
+    } else if (v->mode == MDZCUDA_MODE_GMP) {
+        // mpf_init2(p): precision in limbs P = (max(53,p)+127)/64, storage P+1 limbs
+        const long pb = v->precision < 53 ? 53 : v->precision;
+        n32 = 2 * (int)((pb + 127) / 64 + 1);
+    }
     else { set_err("unknown mode %d", v->mode); return nullptr; }
-    kernel_fn fn = kernel_for_limbs(n32);
+    const bool gmp = v->mode == MDZCUDA_MODE_GMP;
+    kernel_fn fn = gmp ? gmp_kernel_for_limbs(n32 / 2) : kernel_for_limbs(n32);
     if (!fn) { set_err("precision %ld needs %d limbs: no kernel instantiated", v->precision, n32); return nullptr; }
 
     mdzcuda_plan* pl = new mdzcuda_plan();
@@ -256,11 +338,13 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
         for (int k = 0; k < v->aa_factor; ++k) pl->line_map.push_back(b * v->aa_factor + k);
     pl->local_lines = (int)pl->line_map.size();
     pl->nbands = pl->local_lines / v->aa_factor;
-    pl->rc = make_round_cfg(n32, v->mode == MDZCUDA_MODE_LD ? 64 : (int)v->precision);
+    pl->gmp = gmp;
+    pl->rc = make_round_cfg(n32, v->mode == MDZCUDA_MODE_LD ? 64 : (gmp ? 32 * n32 : (int)v->precision));
 
     HostTable xs, ys, jc;
     int ok = (v->mode == MDZCUDA_MODE_LD) ? prologue_ld(v, pl->line_map, xs, ys, jc)
-                                          : prologue_mpfr(v, pl->line_map, xs, ys, jc, n32);
+           : gmp ? prologue_gmp(v, pl->line_map, xs, ys, jc, n32)
+                 : prologue_mpfr(v, pl->line_map, xs, ys, jc, n32);
     if (!ok) { delete pl; return nullptr; }
 
     {
@@ -280,7 +364,7 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
         CUDA_OKP(cudaFuncGetAttributes(&fa, (const void*)fn));
         cudaDeviceProp prop;
         CUDA_OKP(cudaGetDeviceProperties(&prop, device));
-        const int smem = (4 * n32 + 2) * kBlock * (int)sizeof(uint32_t);   // c_re, c_im, shifter scratch
+        const int smem = gmp ? 0 : (4 * n32 + 2) * kBlock * (int)sizeof(uint32_t);   // c_re, c_im, shifter scratch
         if (smem > 48 * 1024)
             CUDA_OKP(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ = 0;
@@ -352,7 +436,7 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         long long need = (npx + kBlock - 1) / kBlock;
         if (grid > need) grid = need;
         pl->info.grid_blocks = (int)grid;
-        kernel_fn fn = kernel_for_limbs(pl->n32);
+        kernel_fn fn = pl->gmp ? gmp_kernel_for_limbs(pl->n32 / 2) : kernel_for_limbs(pl->n32);
         fn<<<(unsigned)grid, kBlock, pl->info.shared_bytes, st>>>(p);
         CUDA_OK(cudaGetLastError());
     }

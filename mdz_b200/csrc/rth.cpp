@@ -246,7 +246,12 @@ static void* rth_render_main(void* ptr)
             flags[i].assign(mdzcuda_plan_bands_total(plans[i]) + 1, 0);
             seen[i].assign(flags[i].size(), 0);
         }
-        int published = 0;
+        // Bands finish out of order on the device(s) but are published strictly in
+        // line order: the reference's consumers (render.c:49-92, main_gui.c:533-599)
+        // clip their window with the *count* of finished lines, which only works
+        // when that count describes a prefix of the image.
+        std::vector<unsigned char> ready(total_bands + 1, 0);
+        int published = 0, fetched = 0;
         bool cancelled = false;
         struct timespec nap = { 0, 200 * 1000 };              // 0.2 ms between polls
         while (published < total_bands) {
@@ -264,14 +269,16 @@ static void* rth_render_main(void* ptr)
                     int e = b;
                     while (e < nb && flags[i][e] && !seen[i][e]) ++e;
                     if (!mdzcuda_plan_fetch_bands(plans[i], img->raw_data, b, e - b)) { err = mdzcuda_last_error(); break; }
-                    for (int k = b; k < e; ++k) { seen[i][k] = 1; publish_band(rth, i + k * ndev); ++published; }
+                    for (int k = b; k < e; ++k) { seen[i][k] = 1; ready[i + k * ndev] = 1; ++fetched; }
                     progress = true;
                     b = e;
                 }
             }
             if (!err.empty()) break;
+            while (published < total_bands && ready[published]) publish_band(rth, published++);
             if (!progress) nanosleep(&nap, 0);
         }
+        (void)fetched;
         for (int i = 0; i < ndev; ++i) mdzcuda_plan_wait(plans[i]);
     }
     for (size_t i = 0; i < plans.size(); ++i) mdzcuda_plan_destroy(plans[i]);
@@ -302,6 +309,13 @@ extern "C" void rth_ui_start_render(rthdata* rth)
     rthpridata* d = rth->data;
     memset(rth->lines_drawn, 0, (size_t)rth->img->user_height);
     rth->min_line_drawn = 0;
+    // The reference clears `started` in the watch thread after it has taken the start
+    // signal (render_threads.c:206-208), so a caller that goes straight on to
+    // rth_ui_wait_until_started can see the previous render's flag.  Clearing it here
+    // closes that window; the new render thread sets it once its state is reset.
+    pthread_mutex_lock(&d->started_mutex);
+    d->started = 0;
+    pthread_mutex_unlock(&d->started_mutex);
     pthread_mutex_lock(&d->start_mutex);
     d->start = 1;
     pthread_cond_signal(&d->start_cond);

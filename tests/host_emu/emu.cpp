@@ -94,3 +94,72 @@ extern "C" void emu_counts(unsigned long long* out, int reset)
 {
     for (int i = 0; i < CNT_N; ++i) { out[i] = g_counts[i]; if (reset) g_counts[i] = 0; }
 }
+
+// ---- GMP mpf mode ---------------------------------------------------------------
+#include "../../mdz_b200/csrc/mpf_sf.cuh"
+
+template <int NL>
+static int gmp_op(int op, const uint64_t* al, long ae, int as, const uint64_t* bl, long be, int bs,
+                  uint64_t* rl, long* re, int* rs)
+{
+    Mpf<NL> a, b, r;
+    for (int i = 0; i < NL; ++i) { a.l[i] = al[i]; b.l[i] = bl[i]; }
+    a.e = (int32_t)ae; a.s = as < 0; b.e = (int32_t)be; b.s = bs < 0;
+    if (as == 0) gset_zero(a);
+    if (bs == 0) gset_zero(b);
+    switch (op) {
+    case 0: gmul<NL>(a, b, r); break;
+    case 1: gmul2<NL>(a, r); break;
+    case 2: gadd<NL>(a, b, r, false); break;
+    case 3: gadd<NL>(a, b, r, true); break;
+    case 4: *rs = ggt4<NL>(a) ? 1 : 0; return 1;
+    default: return 0;
+    }
+    for (int i = 0; i < NL; ++i) rl[i] = r.l[i];
+    *re = r.e; *rs = gz(r) ? 0 : (r.s ? -1 : 1);
+    return 1;
+}
+
+#define GCASE(n) case n: return gmp_op<n>(op, al, ae, as, bl, be, bs, rl, re, rs);
+extern "C" int emu_gmp_op(int op, int nl, const uint64_t* al, long ae, int as,
+                          const uint64_t* bl, long be, int bs, uint64_t* rl, long* re, int* rs)
+{
+    switch (nl) {
+    GCASE(3) GCASE(4) GCASE(5) GCASE(6) GCASE(7) GCASE(8) GCASE(9) GCASE(10) GCASE(11) GCASE(12)
+    GCASE(13) GCASE(14) GCASE(15) GCASE(16) GCASE(17) GCASE(18)
+    default: return 0;
+    }
+}
+
+template <int NL>
+static long gmp_pixel(int fractal, long depth, const uint64_t* const* l, const long* ex, const int* sg)
+{
+    Mpf<NL> v[4];
+    for (int k = 0; k < 4; ++k) {
+        for (int i = 0; i < NL; ++i) v[k].l[i] = l[k][i];
+        v[k].e = (int32_t)ex[k]; v[k].s = sg[k] < 0;
+        if (sg[k] == 0) gset_zero(v[k]);
+    }
+    GmpPixel<NL> st;
+    gmp_pixel_init<NL>(st, v[0], v[1], v[2], v[3]);
+    const bool abs_im = fractal == FRACTAL_BURNING_SHIP;
+    const int abs_re = fractal == FRACTAL_GENERALIZED_CELTIC ? 1 : fractal == FRACTAL_VARIANT ? 2 : 0;
+    while (st.iter < depth)
+        if (gmp_pixel_step<NL>(st, abs_im, abs_re)) return st.iter;
+    return 0;
+}
+
+#define GPCASE(n) case n: return gmp_pixel<n>(fractal, depth, l, ex, sg);
+extern "C" long emu_gmp_pixel(int nl, int fractal, long depth,
+                              const uint64_t* xl, long xe, int xs, const uint64_t* yl, long ye, int ys,
+                              const uint64_t* cxl, long cxe, int cxs, const uint64_t* cyl, long cye, int cys)
+{
+    const uint64_t* l[4] = {xl, yl, cxl, cyl};
+    const long ex[4] = {xe, ye, cxe, cye};
+    const int sg[4] = {xs, ys, cxs, cys};
+    switch (nl) {
+    GPCASE(3) GPCASE(4) GPCASE(5) GPCASE(6) GPCASE(7) GPCASE(8) GPCASE(9) GPCASE(10) GPCASE(11) GPCASE(12)
+    GPCASE(13) GPCASE(14) GPCASE(15) GPCASE(16) GPCASE(17) GPCASE(18)
+    default: return -1;
+    }
+}

@@ -60,5 +60,61 @@ def port_render(view, threads=None):
     return out
 
 
+class OracleMpf(C.Structure):
+    _fields_ = [("sign", C.c_int), ("exp", C.c_long), ("n", C.c_int), ("limbs", C.POINTER(C.c_uint64))]
+
+
+def to_mpf(v, keep):
+    """mdz_b200.mp.Mpf -> OracleMpf."""
+    sg, e, limbs = v.parts()
+    arr = (C.c_uint64 * max(1, len(limbs)))(*limbs)
+    keep.append(arr)
+    return OracleMpf(sg, e, len(limbs), C.cast(arr, C.POINTER(C.c_uint64)))
+
+
+def gmp_tables(view):
+    """fractal_gmp_calculate_line's set-up (fractal.c:299-328) with libgmp itself: x per column, y per line."""
+    from mdz_b200.mp import Mpf, mpf_set, mpf_set_si, mpf_mul, mpf_add, mpf_sub, mpf_div, mpf_ui_div, mpf_mul_ui
+    p = view.precision
+    rw, xmin, width, t1 = Mpf(p), Mpf(p), Mpf(p), Mpf(p)
+    mpf_set_si(rw.ref, view.real_width)
+    mpf_set(xmin.ref, view.gxmin.ref)
+    mpf_set(width.ref, view.gwidth.ref)
+    xs, ys = [], []
+    for ix in range(view.real_width):
+        x = Mpf(p)
+        mpf_ui_div(t1.ref, ix, rw.ref)
+        mpf_mul(x.ref, t1.ref, width.ref)
+        mpf_add(x.ref, x.ref, xmin.ref)
+        xs.append(x)
+    for line in range(view.real_height):
+        y = Mpf(p)
+        mpf_div(t1.ref, width.ref, rw.ref)
+        mpf_mul_ui(t1.ref, t1.ref, line)
+        mpf_sub(y.ref, view.gymax.ref, t1.ref)
+        ys.append(y)
+    return xs, ys
+
+
 def port_render_gmp(view, threads=None):
-    raise NotImplementedError("GMP mpf mode of the C oracle")
+    from mdz_b200.mp import Mpf
+    from mdz_b200.coords import mpfr_to_decimal
+    lib = load()
+    lib.oracle_render_gmp.argtypes = [C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int,
+                                      C.POINTER(OracleMpf), C.POINTER(OracleMpf),
+                                      C.POINTER(OracleMpf), C.POINTER(OracleMpf), C.c_void_p]
+    xs, ys = gmp_tables(view)
+    keep = []
+    xa = (OracleMpf * len(xs))(*[to_mpf(v, keep) for v in xs])
+    ya = (OracleMpf * len(ys))(*[to_mpf(v, keep) for v in ys])
+    jre = jim = None
+    if view.family == 1:
+        # mpfr_to_gmp through "%.Re" (fractal.c:341-342, my_mpfr_to_str.c:68)
+        jre = C.pointer(to_mpf(Mpf(view.precision, mpfr_to_decimal(view.julia_re, False)), keep))
+        jim = C.pointer(to_mpf(Mpf(view.precision, mpfr_to_decimal(view.julia_im, False)), keep))
+    P = (max(53, view.precision) + 127) // 64
+    out = np.full((view.real_height, view.real_width), -1, dtype=np.int32)
+    ok = lib.oracle_render_gmp(P, view.family, view.fractal, view.depth, view.real_width, view.real_height,
+                               xa, ya, jre, jim, out.ctypes.data_as(C.c_void_p))
+    assert ok == 1
+    return out

@@ -43,8 +43,6 @@ def test_reference_cmdline_on_libmdzcuda(name, tmp_path):
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/mdz_cuda not built")
     view, info = G.view_of(meta)
-    if view.mode == 2:
-        pytest.skip("GMP mpf mode: kernel not built yet")
     got_raw, got_rgb = run_cmdline(exe, meta, tmp_path)
     assert np.array_equal(got_raw, raw), "%d raw pixels differ" % int((got_raw != raw).sum())
     if info["palette"] is not None:          # without an embedded palette MDZ seeds rand() from the clock

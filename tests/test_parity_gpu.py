@@ -80,3 +80,52 @@ def test_band_partition_equals_whole(ref_lib):
         p = mdz_b200.Plan(v, 0, first, 3)
         p.launch(); p.fetch(parts); p.close()
     assert (parts == whole).all()
+
+
+# ---- GMP mpf mode (fractal_gmp_calculate_line, fractal.c:260-397) ----------------------
+def check_gmp(view, ref_lib, threads=None):
+    """North-star bar for GMP mode: >= 99.9 % identical, every mismatch reported.
+    The observed result is 100 %, so this asserts exact equality and prints the
+    mismatch set if that ever stops being true."""
+    got = mdz_b200.render(view)
+    want, _ = ref_render(ref_lib, view, threads)
+    bad = np.argwhere(got != want)
+    if bad.size:
+        for y, x in bad[:20]:
+            print("mismatch at line %d px %d: cuda %d reference %d" % (y, x, got[y, x], want[y, x]))
+    assert bad.size == 0, "%d of %d pixels differ (%.4f %%)" % (len(bad), got.size, 100.0 * len(bad) / got.size)
+    return got
+
+
+@pytest.mark.parametrize("prec", [80, 128, 200, 256, 320, 512])
+def test_gmp_precisions_seahorse(ref_lib, prec):
+    check_gmp(make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", 96, 72, mode="gmp", precision=prec, depth=1500), ref_lib)
+
+
+@pytest.mark.parametrize("fractal", [MANDELBROT, BURNING_SHIP, GENERALIZED_CELTIC, VARIANT])
+@pytest.mark.parametrize("prec", [128, 320])
+def test_gmp_fractals(ref_lib, fractal, prec):
+    check_gmp(make_view("-0.5", "-0.3", "3.5", 96, 72, mode="gmp", precision=prec, depth=300, fractal=fractal), ref_lib)
+
+
+def test_gmp_julia_one_digit_constant(ref_lib):
+    # the reference converts the Julia constant per pixel through "%.Re" (fractal.c:341-342),
+    # one significant digit on MPFR 4: -0.8 stays -0.8, 0.156 becomes 0.2.  That conversion
+    # goes through a static buffer shared by all workers (my_mpfr_to_str.c:6), so the
+    # reference itself is only deterministic with ONE thread in this mode: two 8-thread
+    # runs of the unmodified reference differ from each other in ~20 % of the pixels.
+    check_gmp(make_view("0", "0", "3.2", 96, 72, mode="gmp", precision=128, depth=300,
+                        family=FAMILY_JULIA, julia=("-0.8", "0.156")), ref_lib, threads=1)
+
+
+def test_gmp_real_axis_and_aa(ref_lib):
+    check_gmp(make_view("-0.75", "0.0", "2.5", 48, 36, mode="gmp", precision=128, depth=400, aa=2), ref_lib)
+
+
+def test_gmp_deep_zoom_512(ref_lib):
+    # BASELINE configs[3] in miniature: 1e-120 wide window, 512-bit mpf
+    cx = "-1.7400623825793399052208441670658256382966417204361718668798624184611829" \
+         "1966513096674796282803698889934592955622845248"
+    check_gmp(make_view(cx, "0.0281753397792110489924115211443195096875390767429906085704013095958801" 
+                        "743240920186385400814658560553615695084486774077", "1e-120", 48, 27,
+                        mode="gmp", precision=512, depth=3000), ref_lib)

@@ -81,3 +81,79 @@ def test_pixels_match_reference(emu, ref_lib, name, mk, count, spec):
         ix, line = (k * 37 + 5) % W, (k * 53 + (H // 2 if k % 4 == 0 else 3)) % H
         x, y = coords(view, ix, line)
         assert emu_pixel(emu, view, x, y, spec) == ref_pixel(ref_lib, view, x, y), (name, ix, line)
+
+
+# ---- GMP mpf mode: mpf_sf.cuh gmp_pixel_* vs the reference's frac_*_gmp -------------
+from mdz_b200.mp import (MpfStruct, Mpf, mpf_init2, mpf_set, mpf_set_si, mpf_mul, mpf_add, mpf_sub,
+                         mpf_div, mpf_ui_div, mpf_mul_ui)
+
+GFRAC = {MANDELBROT: "frac_mandel_gmp", BURNING_SHIP: "frac_burning_ship_gmp",
+         GENERALIZED_CELTIC: "frac_generalized_celtic_gmp", VARIANT: "frac_variant_gmp"}
+GP = C.POINTER(MpfStruct)
+
+
+def gmp_coords(view, ix, line):
+    """fractal.c:299-328 with the real libgmp."""
+    p = view.precision
+    rw, xmin, width, t1, x, y = (Mpf(p) for _ in range(6))
+    mpf_set_si(rw.ref, view.real_width)
+    mpf_set(xmin.ref, view.gxmin.ref)
+    mpf_set(width.ref, view.gwidth.ref)
+    mpf_ui_div(t1.ref, ix, rw.ref)
+    mpf_mul(x.ref, t1.ref, width.ref)
+    mpf_add(x.ref, x.ref, xmin.ref)
+    mpf_div(t1.ref, width.ref, rw.ref)
+    mpf_mul_ui(t1.ref, t1.ref, line)
+    mpf_sub(y.ref, view.gymax.ref, t1.ref)
+    return x, y
+
+
+def gmp_ref_pixel(ref, view, x, y):
+    p = view.precision
+    fn = getattr(ref, GFRAC[view.fractal])
+    fn.restype = C.c_long
+    fn.argtypes = [C.c_long] + [GP] * 8
+    vals = [Mpf(p) for _ in range(8)]       # bail wim wre cim cre wim2 wre2 t1
+    bail, wim, wre, cim, cre, wim2, wre2, t1 = vals
+    mpf_set_si(bail.ref, 4)
+    for dst, src in ((wim, y), (wre, x), (cim, y), (cre, x)):
+        mpf_set(dst.ref, src.ref)
+    mpf_mul(wim2.ref, y.ref, y.ref)
+    mpf_mul(wre2.ref, x.ref, x.ref)
+    return fn(view.depth, bail.ptr, wim.ptr, wre.ptr, cim.ptr, cre.ptr, wim2.ptr, wre2.ptr, t1.ptr)
+
+
+def fixed_mpf(v, nl):
+    sg, e, limbs = v.parts()
+    out = [0] * nl
+    for i, w in enumerate(limbs):
+        out[nl - len(limbs) + i] = w
+    return (C.c_uint64 * nl)(*out), e, sg
+
+
+GCASES = [
+    ("seahorse gmp 128", lambda: make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", 96, 72, mode="gmp", precision=128, depth=1500), 60),
+    ("seahorse gmp 512", lambda: make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", 96, 72, mode="gmp", precision=512, depth=1500), 16),
+    ("full set gmp 80", lambda: make_view("-0.5", "0.0", "4.0", 96, 72, mode="gmp", precision=80, depth=400), 200),
+    ("ship gmp 256", lambda: make_view("-0.5", "-0.3", "3.5", 96, 72, mode="gmp", precision=256, depth=300, fractal=BURNING_SHIP), 100),
+    ("celtic gmp 320", lambda: make_view("-0.5", "-0.3", "3.5", 96, 72, mode="gmp", precision=320, depth=300, fractal=GENERALIZED_CELTIC), 100),
+    ("hybrid gmp 128", lambda: make_view("-0.5", "-0.3", "3.5", 96, 72, mode="gmp", precision=128, depth=300, fractal=VARIANT), 100),
+    ("real axis gmp 128", lambda: make_view("-0.75", "0.0", "2.5", 64, 48, mode="gmp", precision=128, depth=500), 64),
+]
+
+
+@pytest.mark.parametrize("name,mk,count", GCASES, ids=[c[0] for c in GCASES])
+def test_gmp_pixels_match_reference(emu_lib, ref_lib, name, mk, count):
+    emu_lib.emu_gmp_pixel.restype = C.c_long
+    emu_lib.emu_gmp_pixel.argtypes = [C.c_int, C.c_int, C.c_long] + [U, C.c_long, C.c_int] * 4
+    view = mk()
+    nl = (max(53, view.precision) + 127) // 64 + 1
+    W, H = view.real_width, view.real_height
+    for k in range(count):
+        ix, line = (k * 37 + 5) % W, (k * 53 + (H // 2 if k % 4 == 0 else 3)) % H
+        x, y = gmp_coords(view, ix, line)
+        args = []
+        for v in (x, y, x, y):
+            args += list(fixed_mpf(v, nl))
+        got = emu_lib.emu_gmp_pixel(nl, view.fractal, view.depth, *args)
+        assert got == gmp_ref_pixel(ref_lib, view, x, y), (name, ix, line)
