@@ -97,7 +97,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """Reference arm: the unmodified reference pool on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -138,7 +138,7 @@ def run_reference(args):
                                    "reference pthread pool with -t %d" % (iters, cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def side_precisions(torch, device):
@@ -174,6 +174,14 @@ def side_precisions(torch, device):
 
 
 def main():
+    # rank 0 must print exactly ONE line on stdout; NCCL / torch may write banners to fd 1
+    # ("NCCL version ..."), so park the real stdout and send everything else to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -184,7 +192,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
 
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
         return
 
     import numpy as np
@@ -315,7 +323,7 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)}
         if not args.no_side and world == 1:
             line["per_precision"] = side_precisions(torch, local)
-        print(json.dumps(line))
+        emit(line)
     plan.close()
     if world > 1:
         dist.destroy_process_group()

@@ -123,6 +123,27 @@ int mdzcuda_plan_fetch(mdzcuda_plan*, int32_t* raw_host);
 void* mdzcuda_plan_device_raw(mdzcuda_plan*);
 int   mdzcuda_plan_local_lines(mdzcuda_plan*);
 
+/*
+ * Colour epilogue (optional).  With colour parameters set before a launch, the warp
+ * that completes a band of aa_factor lines colours it on the spot -- palette lookup
+ * or interpolation, anti-aliasing box average and pal_offset exactly as
+ * palette_apply (src/palette.c:406-463), get_pixel_colour (:466-503) and
+ * do_anti_aliasing (src/render.c:108-158) do -- into a device rgb buffer
+ * ([user_height][user_width] guint32, R | G<<8 | B<<16).  mdzcuda_plan_recolour
+ * re-runs only that step from the resident iteration counts (palette cycling,
+ * src/main_gui.c:200-219).  Passing NULL switches the epilogue off again.
+ */
+typedef struct mdzcuda_colour {
+    const uint32_t* palette;    /* globals.c:3 `palette`, pal_indexes entries   */
+    int    pal_indexes;         /* palette.c:15, 2..256                         */
+    int    pal_offset;          /* palette.c:14                                 */
+    double colour_scale;        /* img->colour_scale                            */
+    int    palette_ip;          /* img->palette_ip                              */
+} mdzcuda_colour;
+int mdzcuda_plan_set_colour(mdzcuda_plan*, const mdzcuda_colour*);
+int mdzcuda_plan_recolour(mdzcuda_plan*, void* cuda_stream);
+int mdzcuda_plan_fetch_rgb(mdzcuda_plan*, uint32_t* rgb_host /* user_width*user_height */);
+
 /* Static facts about the kernel chosen for this plan (for reports). */
 typedef struct mdzcuda_kernel_info {
     int limbs;              /* 32-bit limbs of significand                */

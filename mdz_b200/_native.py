@@ -31,6 +31,12 @@ class View(C.Structure):
     ]
 
 
+class Colour(C.Structure):
+    """struct mdzcuda_colour (include/mdzcuda.h)."""
+    _fields_ = [("palette", C.POINTER(C.c_uint32)), ("pal_indexes", C.c_int), ("pal_offset", C.c_int),
+                ("colour_scale", C.c_double), ("palette_ip", C.c_int)]
+
+
 class KernelInfo(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "limbs", "regs_per_thread", "local_bytes", "shared_bytes",
@@ -51,6 +57,9 @@ SYMBOLS = {
     "mdzcuda_plan_fetch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mdzcuda_plan_poll_bands": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mdzcuda_plan_fetch_bands": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "mdzcuda_plan_set_colour": (C.c_int, [C.c_void_p, C.POINTER(Colour)]),
+    "mdzcuda_plan_recolour": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mdzcuda_plan_fetch_rgb": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mdzcuda_plan_device_raw": (C.c_void_p, [C.c_void_p]),
     "mdzcuda_plan_local_lines": (C.c_int, [C.c_void_p]),
     "mdzcuda_plan_kernel_info": (C.c_int, [C.c_void_p, C.POINTER(KernelInfo)]),

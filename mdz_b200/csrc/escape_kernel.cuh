@@ -17,6 +17,7 @@
 #pragma once
 #include "escape_step.cuh"
 #include "mpf_sf.cuh"
+#include "colour.cuh"
 
 namespace mdz {
 
@@ -50,9 +51,34 @@ struct EscapeParams {
     int fractal;
     int chunk;              // iterations between refills
     int spec;               // 1: try the speculative branch-free iteration first
+    ColourParams colour;    // fused epilogue: colour a band as soon as it completes (enabled = 0: raw only)
 };
 
 constexpr int kBlock = 128;
+
+// Warp-level completion of bands: every lane passes the band it just completed (or
+// -1).  All writers fenced before bumping the band counter, so after this fence the
+// band's raw values are visible; they are read past L1 (__ldcg) by colour_band.
+__device__ __forceinline__ bool publish_bands(const EscapeParams& p, int finished_band, unsigned lane)
+{
+    unsigned fin = __ballot_sync(0xffffffffu, finished_band >= 0);
+    if (!fin) return false;
+    __threadfence();
+    while (fin) {
+        const int src = __ffs(fin) - 1;
+        fin &= fin - 1;
+        const int band = __shfl_sync(0xffffffffu, finished_band, src);
+        if (p.colour.enabled)
+            colour_band(p.raw + (size_t)band * p.aa * p.width, p.width, p.aa, band, p.colour, lane);
+        __syncwarp();
+        __threadfence();
+        if (lane == 0) {
+            p.band_flag[band] = 1;
+            atomicAdd((unsigned int*)p.bands_done, 1u);
+        }
+    }
+    return true;
+}
 
 template <int N>
 __device__ __forceinline__ void load_entry(const CoordTable& t, int i, Num<N>& v)
@@ -94,6 +120,7 @@ escape_mpfr_kernel(const EscapeParams p)
     st.cre_e = E_ZERO; st.cim_e = E_ZERO; st.cre_s = 0; st.cim_s = 0; st.iter = 0;
 
     bool active = false;
+    int finished_band = -1;
     bool exhausted = false;         // warp-uniform
     bool use_spec = SpecLimbs<N>::value && p.spec != 0;     // warp-uniform
     int spec_pause = 0, spec_backoff = 8;
@@ -155,13 +182,12 @@ escape_mpfr_kernel(const EscapeParams p)
                     active = false;
                     const unsigned band = (pix / (unsigned)p.width) / (unsigned)p.aa;
                     const unsigned done = atomicAdd(&p.band_count[band], 1u) + 1u;
-                    if (done == (unsigned)p.width * (unsigned)p.aa) {
-                        __threadfence();
-                        p.band_flag[band] = 1;
-                        atomicAdd((unsigned int*)p.bands_done, 1u);
-                    }
+                    if (done == (unsigned)p.width * (unsigned)p.aa) finished_band = (int)band;
                 }
             }
+            // a lane that completed a band hands it to the whole warp: colour it (fused
+            // epilogue), then publish the band flag the host polls
+            if (publish_bands(p, finished_band, lane)) finished_band = -1;
             if (!__any_sync(0xffffffffu, active)) break;
         }
         // ---- adapt: speculation is only worth it while fall-backs are scarce ----
@@ -209,6 +235,7 @@ escape_gmp_kernel(const EscapeParams p)
     GmpPixel<NL> st;
     st.iter = 0;
     bool active = false;
+    int finished_band = -1;
     bool exhausted = false;
     unsigned pix = 0;
     const bool abs_im = p.fractal == FRACTAL_BURNING_SHIP;
@@ -256,13 +283,12 @@ escape_gmp_kernel(const EscapeParams p)
                     active = false;
                     const unsigned band = (pix / (unsigned)p.width) / (unsigned)p.aa;
                     const unsigned done = atomicAdd(&p.band_count[band], 1u) + 1u;
-                    if (done == (unsigned)p.width * (unsigned)p.aa) {
-                        __threadfence();
-                        p.band_flag[band] = 1;
-                        atomicAdd((unsigned int*)p.bands_done, 1u);
-                    }
+                    if (done == (unsigned)p.width * (unsigned)p.aa) finished_band = (int)band;
                 }
             }
+            // a lane that completed a band hands it to the whole warp: colour it (fused
+            // epilogue), then publish the band flag the host polls
+            if (publish_bands(p, finished_band, lane)) finished_band = -1;
             if (!__any_sync(0xffffffffu, active)) break;
         }
     }

@@ -151,6 +151,9 @@ struct mdzcuda_plan {
     bool gmp = false;
     mdzcuda_kernel_info info;
     unsigned int* h_pinned = nullptr;   // 4 words of pinned staging
+    uint32_t* d_palette = nullptr;      // 256 entries
+    uint32_t* d_rgb = nullptr;          // [nbands][user_width]
+    ColourParams colour;                // enabled = 0 until mdzcuda_plan_set_colour
 };
 
 typedef void (*kernel_fn)(const EscapeParams);
@@ -333,6 +336,7 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
     pl->device = device;
     pl->n32 = n32;
     pl->band_first = band_first; pl->band_stride = band_stride;
+    memset(&pl->colour, 0, sizeof pl->colour);
     const int total_bands = v->real_height / v->aa_factor;
     for (int b = band_first; b < total_bands; b += band_stride)
         for (int k = 0; k < v->aa_factor; ++k) pl->line_map.push_back(b * v->aa_factor + k);
@@ -429,6 +433,7 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         p.fractal = pl->view.fractal;
         p.chunk = pl->chunk ? pl->chunk : default_chunk(pl->n32);
         p.spec = pl->spec;
+        p.colour = pl->colour;
         int bps = pl->blocks_per_sm ? pl->blocks_per_sm : pl->info.blocks_per_sm;
         if (bps > pl->info.blocks_per_sm) bps = pl->info.blocks_per_sm;
         long long npx = (long long)pl->local_lines * pl->view.real_width;
@@ -520,6 +525,57 @@ extern "C" int mdzcuda_plan_fetch_bands(mdzcuda_plan* pl, int32_t* raw_host, int
     return 1;
 }
 
+
+// ---- colour epilogue -------------------------------------------------------------
+extern "C" int mdzcuda_plan_set_colour(mdzcuda_plan* pl, const mdzcuda_colour* c)
+{
+    if (!pl) { set_err("null plan"); return 0; }
+    if (!c) { pl->colour.enabled = 0; return 1; }
+    if (!c->palette || c->pal_indexes < 2 || c->pal_indexes > 256) { set_err("palette needs 2..256 entries"); return 0; }
+    CUDA_OK(cudaSetDevice(pl->device));
+    const int uw = pl->view.real_width / pl->view.aa_factor;
+    if (!pl->d_palette) CUDA_OK(cudaMalloc(&pl->d_palette, 256 * sizeof(uint32_t)));
+    if (!pl->d_rgb) CUDA_OK(cudaMalloc(&pl->d_rgb, ((size_t)pl->nbands * uw + 1) * sizeof(uint32_t)));
+    CUDA_OK(cudaMemcpy(pl->d_palette, c->palette, (size_t)c->pal_indexes * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    pl->colour.palette = pl->d_palette;
+    pl->colour.rgb = pl->d_rgb;
+    pl->colour.scale = c->colour_scale;
+    pl->colour.pal_indexes = c->pal_indexes;
+    pl->colour.pal_offset = c->pal_offset;
+    pl->colour.interpolate = c->palette_ip ? 1 : 0;
+    pl->colour.enabled = 1;
+    return 1;
+}
+
+extern "C" int mdzcuda_plan_recolour(mdzcuda_plan* pl, void* cuda_stream)
+{
+    if (!pl) { set_err("null plan"); return 0; }
+    if (!pl->colour.enabled) { set_err("no colour parameters set"); return 0; }
+    CUDA_OK(cudaSetDevice(pl->device));
+    if (pl->nbands > 0) {
+        const int blocks = (pl->nbands + 3) / 4;
+        recolour_kernel<<<blocks, 128, 0, (cudaStream_t)cuda_stream>>>(pl->d_raw, pl->view.real_width,
+                                                                      pl->view.aa_factor, pl->nbands, pl->colour);
+        CUDA_OK(cudaGetLastError());
+    }
+    CUDA_OK(cudaEventRecord(pl->done_ev, (cudaStream_t)cuda_stream));
+    return 1;
+}
+
+extern "C" int mdzcuda_plan_fetch_rgb(mdzcuda_plan* pl, uint32_t* rgb_host)
+{
+    if (!pl || !rgb_host) { set_err("null argument"); return 0; }
+    if (!pl->colour.enabled) { set_err("no colour parameters set"); return 0; }
+    CUDA_OK(cudaSetDevice(pl->device));
+    CUDA_OK(cudaEventSynchronize(pl->done_ev));
+    const int uw = pl->view.real_width / pl->view.aa_factor;
+    const size_t line_bytes = (size_t)uw * sizeof(uint32_t);
+    if (pl->nbands > 0)
+        CUDA_OK(cudaMemcpy2D(rgb_host + (size_t)pl->band_first * uw, line_bytes * pl->band_stride,
+                             pl->d_rgb, line_bytes, line_bytes, pl->nbands, cudaMemcpyDeviceToHost));
+    return 1;
+}
+
 extern "C" void* mdzcuda_plan_device_raw(mdzcuda_plan* pl) { return pl ? pl->d_raw : nullptr; }
 extern "C" int mdzcuda_plan_local_lines(mdzcuda_plan* pl) { return pl ? pl->local_lines : -1; }
 
@@ -535,6 +591,7 @@ extern "C" void mdzcuda_plan_destroy(mdzcuda_plan* pl)
     if (!pl) return;
     cudaSetDevice(pl->device);
     pl->xs.release(); pl->ys.release(); pl->jc.release();
+    cudaFree(pl->d_palette); cudaFree(pl->d_rgb);
     cudaFree(pl->d_raw); cudaFree(pl->d_ctrl); cudaFree(pl->d_band_count); cudaFree(pl->d_band_flag);
     if (pl->side) cudaStreamDestroy(pl->side);
     if (pl->done_ev) cudaEventDestroy(pl->done_ev);

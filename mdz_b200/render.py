@@ -140,6 +140,25 @@ class Plan:
         self._chk(_l.lib.mdzcuda_plan_fetch(self.h, out.ctypes.data_as(C.c_void_p)), "plan_fetch")
         return out
 
+    def set_colour(self, palette, pal_offset=0, colour_scale=1.0, palette_ip=False):
+        """Switch the fused colour epilogue on (palette: packed R|G<<8|B<<16 ints)."""
+        pal = np.ascontiguousarray(np.asarray(palette, dtype=np.uint32))
+        self._pal = pal
+        c = _l.Colour(pal.ctypes.data_as(C.POINTER(C.c_uint32)), len(pal), int(pal_offset),
+                      float(colour_scale), 1 if palette_ip else 0)
+        self._chk(_l.lib.mdzcuda_plan_set_colour(self.h, C.byref(c)), "plan_set_colour")
+
+    def recolour(self, stream=None):
+        self._chk(_l.lib.mdzcuda_plan_recolour(self.h, C.c_void_p(stream or 0)), "plan_recolour")
+
+    def fetch_rgb(self, out=None):
+        v = self.view
+        if out is None:
+            out = np.zeros((v.user_height, v.user_width), dtype=np.uint32)
+        assert out.dtype == np.uint32 and out.flags["C_CONTIGUOUS"] and out.shape == (v.user_height, v.user_width)
+        self._chk(_l.lib.mdzcuda_plan_fetch_rgb(self.h, out.ctypes.data_as(C.c_void_p)), "plan_fetch_rgb")
+        return out
+
     def kernel_info(self):
         ki = _l.KernelInfo()
         self._chk(_l.lib.mdzcuda_plan_kernel_info(self.h, C.byref(ki)), "plan_kernel_info")
