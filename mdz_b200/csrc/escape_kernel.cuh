@@ -91,7 +91,13 @@ __device__ __forceinline__ void load_entry(const CoordTable& t, int i, Num<N>& v
 
 // limb counts for which the speculative iteration (escape_step.cuh) is compiled in:
 // it keeps the previous state alive for the fall-back, 4N extra registers
-template <int N> struct SpecLimbs { static constexpr bool value = N >= 3 && N <= 10; };
+template <int N> struct SpecLimbs { static constexpr bool value = N >= 3; };
+// ... and from where on its checkpoint lives in shared memory instead of registers
+template <int N> struct SpecSmemCkpt { static constexpr bool value = N > 10; };
+// shared-memory words per thread: c_re, c_im, limb-shifter scratch, checkpoint
+template <int N> struct SmemWords {
+    static constexpr int value = 2 * N + ScratchWords<N>::value + (SpecSmemCkpt<N>::value ? CkptWords<N>::value : 0);
+};
 
 // resident blocks per SM the register allocator is asked to make room for
 template <int N> struct MinBlocks {
@@ -111,6 +117,7 @@ escape_mpfr_kernel(const EscapeParams p)
 #pragma unroll
     for (int k = 0; k < ScratchWords<N>::value; ++k) scr[k * kBlock] = 0u;
     static_assert(kScratchStride == kBlock, "scratch stride must equal the block size");
+    uint32_t* ckpt = csm + (2 * N + ScratchWords<N>::value) * kBlock + threadIdx.x;   // only used when SpecSmemCkpt<N>
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned total = (unsigned)p.width * (unsigned)p.lines;
@@ -172,7 +179,7 @@ escape_mpfr_kernel(const EscapeParams p)
             if (active) {
                 bool esc;
                 if (SpecLimbs<N>::value)
-                    esc = pixel_step_auto<N>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re, use_spec, rare_seen);
+                    esc = pixel_step_auto<N, SpecSmemCkpt<N>::value>(st, cre_m, cim_m, scr, ckpt, p.rc, abs_im, abs_re, use_spec, rare_seen);
                 else
                     esc = pixel_step<N>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re);
                 const int iter = st.iter;

@@ -116,21 +116,67 @@ MDZ_HD bool pixel_step_spec(PixelState<N>& st, const uint32_t* cre_m, const uint
     return esc;
 }
 
+// Checkpoint of the loop-carried state for the speculative step.  For small limb
+// counts it simply stays in registers; for large ones (4N extra registers would cost a
+// resident block) it goes to a per-thread shared-memory column of 4N+5 words.
+template <int N> struct CkptWords { static constexpr int value = 4 * N + 5; };
+
+template <int N>
+MDZ_HD void ckpt_save(const PixelState<N>& st, uint32_t* ck)
+{
+    MDZ_UNROLL
+    for (int k = 0; k < N; ++k) {
+        ck[(0 * N + k) * kScratchStride] = st.wre.m[k];
+        ck[(1 * N + k) * kScratchStride] = st.wim.m[k];
+        ck[(2 * N + k) * kScratchStride] = st.wre2.m[k];
+        ck[(3 * N + k) * kScratchStride] = st.wim2.m[k];
+    }
+    ck[(4 * N + 0) * kScratchStride] = (uint32_t)st.wre.e;
+    ck[(4 * N + 1) * kScratchStride] = (uint32_t)st.wim.e;
+    ck[(4 * N + 2) * kScratchStride] = (uint32_t)st.wre2.e;
+    ck[(4 * N + 3) * kScratchStride] = (uint32_t)st.wim2.e;
+    ck[(4 * N + 4) * kScratchStride] = st.wre.s | (st.wim.s << 1);      // squares are non-negative
+}
+
+template <int N>
+MDZ_HD void ckpt_load(PixelState<N>& st, const uint32_t* ck)
+{
+    MDZ_UNROLL
+    for (int k = 0; k < N; ++k) {
+        st.wre.m[k]  = ck[(0 * N + k) * kScratchStride];
+        st.wim.m[k]  = ck[(1 * N + k) * kScratchStride];
+        st.wre2.m[k] = ck[(2 * N + k) * kScratchStride];
+        st.wim2.m[k] = ck[(3 * N + k) * kScratchStride];
+    }
+    st.wre.e  = (int32_t)ck[(4 * N + 0) * kScratchStride];
+    st.wim.e  = (int32_t)ck[(4 * N + 1) * kScratchStride];
+    st.wre2.e = (int32_t)ck[(4 * N + 2) * kScratchStride];
+    st.wim2.e = (int32_t)ck[(4 * N + 3) * kScratchStride];
+    const uint32_t sg = ck[(4 * N + 4) * kScratchStride];
+    st.wre.s = sg & 1u; st.wim.s = (sg >> 1) & 1u; st.wre2.s = 0; st.wim2.s = 0;
+}
+
 // Speculate when the warp's recent history says it pays (use_spec is
 // warp-uniform and maintained by the kernel), fall back per lane otherwise.
-template <int N>
+// SMEM_CKPT: the previous state is parked in shared memory instead of registers.
+// (Measured alternative, rejected: running the general step out of line from the
+// checkpoint keeps it out of the kernel's register allocation but costs a state
+// round trip per call -- 12% slower at 512 bits on ordinary views, 25% on views
+// that need the general step every iteration.)
+template <int N, bool SMEM_CKPT>
 MDZ_HD bool pixel_step_auto(PixelState<N>& st, const uint32_t* cre_m, const uint32_t* cim_m,
-                            uint32_t* scr, const RoundCfg& rc, bool abs_im, int abs_re,
+                            uint32_t* scr, uint32_t* ckpt, const RoundCfg& rc, bool abs_im, int abs_re,
                             bool use_spec, uint32_t& rare_seen)
 {
     if (use_spec) {
-        const PixelState<N> keep = st;
+        PixelState<N> keep;
+        if (SMEM_CKPT) ckpt_save<N>(st, ckpt); else keep = st;
         uint32_t rare = 0;
         const bool esc = pixel_step_spec<N>(st, cre_m, cim_m, scr, rc, abs_im, abs_re, rare);
         if (rare == 0) return esc;
         MDZ_COUNT(CNT_SPEC_FALLBACK);
         rare_seen += 1;
-        st = keep;
+        if (SMEM_CKPT) { ckpt_load<N>(st, ckpt); st.iter -= 1; } else st = keep;
     }
     return pixel_step<N>(st, cre_m, cim_m, scr, rc, abs_im, abs_re);
 }

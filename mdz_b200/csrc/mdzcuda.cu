@@ -172,6 +172,18 @@ static kernel_fn gmp_kernel_for_limbs(int nl)
     }
 }
 
+static int smem_words_for_limbs(int n)
+{
+    switch (n) {
+    case 2: return SmemWords<2>::value;   case 3: return SmemWords<3>::value;   case 4: return SmemWords<4>::value;
+    case 5: return SmemWords<5>::value;   case 6: return SmemWords<6>::value;   case 7: return SmemWords<7>::value;
+    case 8: return SmemWords<8>::value;   case 9: return SmemWords<9>::value;   case 10: return SmemWords<10>::value;
+    case 11: return SmemWords<11>::value; case 12: return SmemWords<12>::value; case 13: return SmemWords<13>::value;
+    case 14: return SmemWords<14>::value; case 15: return SmemWords<15>::value; case 16: return SmemWords<16>::value;
+    default: return 0;
+    }
+}
+
 static kernel_fn kernel_for_limbs(int n)
 {
     switch (n) {
@@ -368,7 +380,7 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
         CUDA_OKP(cudaFuncGetAttributes(&fa, (const void*)fn));
         cudaDeviceProp prop;
         CUDA_OKP(cudaGetDeviceProperties(&prop, device));
-        const int smem = gmp ? 0 : (4 * n32 + 2) * kBlock * (int)sizeof(uint32_t);   // c_re, c_im, shifter scratch
+        const int smem = gmp ? 0 : smem_words_for_limbs(n32) * kBlock * (int)sizeof(uint32_t);   // c_re, c_im, shifter scratch, checkpoint
         if (smem > 48 * 1024)
             CUDA_OKP(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ = 0;

@@ -70,8 +70,10 @@ static long pixel(long prec, int fractal, long depth, int spec,
     const bool abs_im = fractal == FRACTAL_BURNING_SHIP;
     const int abs_re = fractal == FRACTAL_GENERALIZED_CELTIC ? 1 : fractal == FRACTAL_VARIANT ? 2 : 0;
     uint32_t rare_seen = 0;
+    uint32_t ck[CkptWords<N>::value];
     while (st.iter < depth)
-        if (pixel_step_auto<N>(st, cre, cim, scr, rc, abs_im, abs_re, spec != 0, rare_seen)) return st.iter;
+        if (spec == 2 ? pixel_step_auto<N, true>(st, cre, cim, scr, ck, rc, abs_im, abs_re, true, rare_seen)
+                      : pixel_step_auto<N, false>(st, cre, cim, scr, ck, rc, abs_im, abs_re, spec != 0, rare_seen)) return st.iter;
     return 0;
 }
 
