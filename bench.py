@@ -33,9 +33,19 @@ def macs_per_iteration(n_limbs):
     return 2 * n_limbs * n_limbs + n_limbs
 
 
-def workload_view():
+def workload_view(world=1, scaling="weak"):
+    """BASELINE configs[1] at N=1.  With N ranks the path shards by line bands
+    (no collective), so by default the benchmark is weak-scaled: the same view at
+    N times the pixels (1920x1080 per GPU: 2716x1528 on 2, 3840x2160 on 4,
+    5432x3056 on 8), each rank rendering bands r, r+N, ...  `--scaling strong`
+    keeps the 1920x1080 image and splits it instead."""
     from views import config2
-    return config2(1920, 1080, 10000)
+    if world == 1 or scaling == "strong":
+        return config2(1920, 1080, 10000)
+    f = world ** 0.5
+    w = int(round(1920 * f / 8.0)) * 8
+    h = int(round(1080 * f / 8.0)) * 8
+    return config2(w, h, 10000)
 
 
 def iterations_of(raw, depth):
@@ -188,6 +198,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-side", action="store_true", help="skip the per-precision side measurements")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = same view at N x the pixels (default), strong = split the 1920x1080 image")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
 
@@ -214,7 +226,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    view = workload_view()
+    view = workload_view(world, args.scaling)
     plan = mdz_b200.Plan(view, local, band_first=rank, band_stride=world)
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
@@ -280,11 +292,14 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
             "dtype": "u32 limbs (64-bit significand soft-float == x87 long double)",
             "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: full M-set cx=-0.5 cy=0 size=4, 1920x1080, "
-                                   "long double mode, depth 10000",
+            "config": {"workload": "BASELINE configs[1]: full M-set cx=-0.5 cy=0 size=4, %dx%d, "
+                                   "long double mode, depth 10000%s" % (
+                                       view.real_width, view.real_height,
+                                       "" if world == 1 else (" (weak scaling: 1920x1080 pixels per GPU)" if args.scaling == "weak"
+                                                               else " (strong scaling: one 1920x1080 image split)")),
                        "pixel_iterations_per_step": total_iters,
                        "partition": "interleaved line bands, one plan per rank, no collective",
                        "l2": "256 MiB buffer rewritten between steps (inputs are KB-sized tables)"},
