@@ -115,19 +115,25 @@ struct HostTable {
 struct DevTable {
     uint32_t* m = nullptr; int32_t* e = nullptr; uint32_t* s = nullptr; int count = 0;
     CoordTable view() const { CoordTable t; t.m = m; t.e = e; t.s = s; t.count = count; return t; }
-    void release() { cudaFree(m); cudaFree(e); cudaFree(s); m = nullptr; e = nullptr; s = nullptr; }
 };
 
-static int upload(const HostTable& h, DevTable& d)
+// All small device state of a plan lives in ONE allocation (cudaMalloc / cudaFree cost
+// ~0.1-0.5 ms each and they used to be a dozen per render): the three coordinate tables,
+// the control words, the per-band counters and flags.  One H2D copy fills the tables.
+struct Arena {
+    std::vector<uint32_t> host;     // image of the table part
+    size_t words = 0;
+    size_t reserve(size_t n) { const size_t at = words; words += (n + 3) & ~(size_t)3; return at; }
+};
+
+static size_t arena_put(Arena& a, const HostTable& h, size_t& om, size_t& oe, size_t& os)
 {
-    d.count = h.count;
-    CUDA_OK(cudaMalloc(&d.m, h.m.size() * 4 + 4));
-    CUDA_OK(cudaMalloc(&d.e, h.e.size() * 4 + 4));
-    CUDA_OK(cudaMalloc(&d.s, h.s.size() * 4 + 4));
-    CUDA_OK(cudaMemcpy(d.m, h.m.data(), h.m.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(d.e, h.e.data(), h.e.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(d.s, h.s.data(), h.s.size() * 4, cudaMemcpyHostToDevice));
-    return 1;
+    om = a.reserve(h.m.size()); oe = a.reserve(h.e.size()); os = a.reserve(h.s.size());
+    a.host.resize(a.words, 0u);
+    if (!h.m.empty()) memcpy(&a.host[om], h.m.data(), h.m.size() * 4);
+    if (!h.e.empty()) memcpy(&a.host[oe], h.e.data(), h.e.size() * 4);
+    if (!h.s.empty()) memcpy(&a.host[os], h.s.data(), h.s.size() * 4);
+    return a.words;
 }
 
 // ---------------------------------------------------------------------------
@@ -142,9 +148,11 @@ struct mdzcuda_plan {
     DevTable xs, ys, jc;
     RoundCfg rc;
     int32_t* d_raw = nullptr;
+    uint32_t* d_arena = nullptr;        // tables + everything below
     unsigned int* d_ctrl = nullptr;     // [0] queue, [1] bands_done, [2] cancel
     unsigned int* d_band_count = nullptr;
     unsigned char* d_band_flag = nullptr;
+    size_t reset_words = 0;             // ctrl + band_count + band_flag, contiguous
     cudaStream_t side = nullptr;        // progress / cancel traffic while the kernel runs
     cudaEvent_t done_ev = nullptr;
     int chunk = 0, blocks_per_sm = 0, spec = 1;
@@ -365,16 +373,32 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
 
     {
         CUDA_OKP(cudaSetDevice(device));
-        if (!upload(xs, pl->xs) || !upload(ys, pl->ys) || !upload(jc, pl->jc)) goto fail;
+        {
+            Arena ar;
+            size_t o[9];
+            arena_put(ar, xs, o[0], o[1], o[2]);
+            arena_put(ar, ys, o[3], o[4], o[5]);
+            const size_t table_words = arena_put(ar, jc, o[6], o[7], o[8]);
+            const size_t o_ctrl = ar.reserve(4);
+            const size_t o_count = ar.reserve((size_t)pl->nbands + 1);
+            const size_t o_flag = ar.reserve(((size_t)pl->nbands + 4) / 4 + 1);
+            CUDA_OKP(cudaMalloc(&pl->d_arena, ar.words * sizeof(uint32_t)));
+            CUDA_OKP(cudaMemcpy(pl->d_arena, ar.host.data(), table_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            CUDA_OKP(cudaMemset(pl->d_arena + o_ctrl, 0, (ar.words - o_ctrl) * sizeof(uint32_t)));
+            uint32_t* b = pl->d_arena;
+            pl->xs.m = b + o[0]; pl->xs.e = (int32_t*)(b + o[1]); pl->xs.s = b + o[2]; pl->xs.count = xs.count;
+            pl->ys.m = b + o[3]; pl->ys.e = (int32_t*)(b + o[4]); pl->ys.s = b + o[5]; pl->ys.count = ys.count;
+            pl->jc.m = b + o[6]; pl->jc.e = (int32_t*)(b + o[7]); pl->jc.s = b + o[8]; pl->jc.count = jc.count;
+            pl->d_ctrl = b + o_ctrl;
+            pl->d_band_count = b + o_count;
+            pl->d_band_flag = (unsigned char*)(b + o_flag);
+            pl->reset_words = ar.words - o_ctrl;
+        }
         size_t npx = (size_t)pl->local_lines * v->real_width;
         CUDA_OKP(cudaMalloc(&pl->d_raw, (npx ? npx : 1) * sizeof(int32_t)));
-        CUDA_OKP(cudaMalloc(&pl->d_ctrl, 4 * sizeof(unsigned int)));
-        CUDA_OKP(cudaMemset(pl->d_ctrl, 0, 4 * sizeof(unsigned int)));
-        CUDA_OKP(cudaMalloc(&pl->d_band_count, (pl->nbands + 1) * sizeof(unsigned int)));
-        CUDA_OKP(cudaMalloc(&pl->d_band_flag, pl->nbands + 1));
         CUDA_OKP(cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking));
         CUDA_OKP(cudaEventCreateWithFlags(&pl->done_ev, cudaEventDisableTiming));
-        CUDA_OKP(cudaMallocHost(&pl->h_pinned, 4 * sizeof(unsigned int)));
+        pl->h_pinned = (unsigned int*)calloc(4, sizeof(unsigned int));   // tiny staging words (pageable: cudaMallocHost costs ~1 ms)
 
         cudaFuncAttributes fa;
         CUDA_OKP(cudaFuncGetAttributes(&fa, (const void*)fn));
@@ -424,9 +448,7 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
     if (!pl) { set_err("null plan"); return 0; }
     cudaStream_t st = (cudaStream_t)cuda_stream;
     CUDA_OK(cudaSetDevice(pl->device));
-    CUDA_OK(cudaMemsetAsync(pl->d_ctrl, 0, 4 * sizeof(unsigned int), st));
-    CUDA_OK(cudaMemsetAsync(pl->d_band_count, 0, (pl->nbands + 1) * sizeof(unsigned int), st));
-    CUDA_OK(cudaMemsetAsync(pl->d_band_flag, 0, pl->nbands + 1, st));
+    CUDA_OK(cudaMemsetAsync(pl->d_ctrl, 0, pl->reset_words * sizeof(uint32_t), st));   // queue, counters, flags
     if (pl->local_lines > 0) {
         EscapeParams p;
         p.xs = pl->xs.view(); p.ys = pl->ys.view(); p.jc = pl->jc.view();
@@ -602,12 +624,11 @@ extern "C" void mdzcuda_plan_destroy(mdzcuda_plan* pl)
 {
     if (!pl) return;
     cudaSetDevice(pl->device);
-    pl->xs.release(); pl->ys.release(); pl->jc.release();
     cudaFree(pl->d_palette); cudaFree(pl->d_rgb);
-    cudaFree(pl->d_raw); cudaFree(pl->d_ctrl); cudaFree(pl->d_band_count); cudaFree(pl->d_band_flag);
+    cudaFree(pl->d_raw); cudaFree(pl->d_arena);
     if (pl->side) cudaStreamDestroy(pl->side);
     if (pl->done_ev) cudaEventDestroy(pl->done_ev);
-    if (pl->h_pinned) cudaFreeHost(pl->h_pinned);
+    free(pl->h_pinned);
     delete pl;
 }
 
