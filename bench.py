@@ -160,6 +160,7 @@ def side_precisions(torch, device):
         ("mpfr128", make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", 1920, 1080, precision=128, depth=10000)),
         ("mpfr320", deep_embedded_julia(960, 540)),
         ("mpfr512", make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", 960, 540, precision=512, depth=10000)),
+        ("gmp512", make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", 960, 540, mode="gmp", precision=512, depth=10000)),
     ]
     peak = mdz_b200.imad_peak(device, 100)
     peak32 = mdz_b200.imad_peak(device, 100, wide=False)
@@ -173,12 +174,15 @@ def side_precisions(torch, device):
         iters = iterations_of(plan.fetch(), view.depth)
         ki = plan.kernel_info()
         rate = iters / (ms * 1e-3)
+        # GMP mode multiplies the top P 64-bit limbs of each operand: N = 2P words
+        n_mac = ki["limbs"] - 2 if view.mode == 2 else ki["limbs"]
         out[name] = {"value": rate, "unit": UNIT, "ms": ms, "pixel_iterations": iters,
                      "view": "%dx%d" % (view.real_width, view.real_height),
-                     "limbs": ki["limbs"], "regs": ki["regs_per_thread"], "spill_bytes": ki["local_bytes"],
+                     "limbs": ki["limbs"], "mac_limbs": n_mac, "macs_per_iteration": macs_per_iteration(n_mac),
+                     "regs": ki["regs_per_thread"], "spill_bytes": ki["local_bytes"],
                      "blocks_per_sm": ki["blocks_per_sm"],
-                     "imad_frac": rate * macs_per_iteration(ki["limbs"]) / peak,
-                     "frac_of_imad32_issue": rate * macs_per_iteration(ki["limbs"]) / peak32}
+                     "imad_frac": rate * macs_per_iteration(n_mac) / peak,
+                     "frac_of_imad32_issue": rate * macs_per_iteration(n_mac) / peak32}
         plan.close()
     return out
 

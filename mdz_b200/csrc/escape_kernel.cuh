@@ -17,6 +17,7 @@
 #pragma once
 #include "escape_step.cuh"
 #include "mpf_sf.cuh"
+#include "mpf_fast.cuh"
 #include "colour.cuh"
 
 namespace mdz {
@@ -295,6 +296,97 @@ escape_gmp_kernel(const EscapeParams p)
             }
             // a lane that completed a band hands it to the whole warp: colour it (fused
             // epilogue), then publish the band flag the host polls
+            if (publish_bands(p, finished_band, lane)) finished_band = -1;
+            if (!__any_sync(0xffffffffu, active)) break;
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------
+// GMP mpf mode, fast kernel: mpf_fast.cuh (register-resident 32-bit words,
+// IMAD.WIDE high products, shared-memory limb shifter).  NW = 2*(P+1) words.
+// Shared memory per thread: c_re, c_im (2*NW) + shifter column (3*NW).
+// ---------------------------------------------------------------------------
+template <int NW> struct GSmemWords { static constexpr int value = 2 * NW + GScratchWords<NW>::value; };
+template <int NW> struct GMinBlocks { static constexpr int value = NW <= 8 ? 6 : NW <= 12 ? 4 : 3; };
+
+template <int NW>
+__device__ __forceinline__ void load_gf_entry(const CoordTable& t, int i, GF<NW>& v)
+{
+#pragma unroll
+    for (int k = 0; k < NW; ++k) v.m[k] = __ldg(&t.m[(size_t)k * t.count + i]);
+    v.e = __ldg(&t.e[i]);
+    v.s = __ldg(&t.s[i]);
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kBlock, GMinBlocks<NW>::value)
+escape_gmpf_kernel(const EscapeParams p)
+{
+    extern __shared__ uint32_t csm[];
+    uint32_t* cre_m = csm + threadIdx.x;
+    uint32_t* cim_m = csm + NW * kBlock + threadIdx.x;
+    uint32_t* scr = csm + 2 * NW * kBlock + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < GScratchWords<NW>::value; ++k) scr[k * kBlock] = 0u;
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned total = (unsigned)p.width * (unsigned)p.lines;
+    GFPixel<NW> st;
+    st.iter = 0;
+    bool active = false;
+    int finished_band = -1;
+    bool exhausted = false;
+    unsigned pix = 0;
+    const bool abs_im = p.fractal == FRACTAL_BURNING_SHIP;
+    const int  abs_re = p.fractal == FRACTAL_GENERALIZED_CELTIC ? 1
+                      : p.fractal == FRACTAL_VARIANT ? 2 : 0;
+    for (;;) {
+        {
+            int stop = 0;
+            if (lane == 0) stop = *p.cancel;
+            if (__shfl_sync(0xffffffffu, stop, 0)) break;
+        }
+        if (!exhausted) {
+            const unsigned need = __ballot_sync(0xffffffffu, !active);
+            if (need) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(p.queue, (unsigned)__popc(need));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base + (unsigned)__popc(need) >= total) exhausted = true;
+                if (!active) {
+                    const unsigned idx = base + (unsigned)__popc(need & ((1u << lane) - 1u));
+                    if (idx < total) {
+                        pix = idx;
+                        const int line = (int)(idx / (unsigned)p.width);
+                        const int ix = (int)(idx - (unsigned)line * (unsigned)p.width);
+                        GF<NW> x, y, cx, cy;
+                        load_gf_entry<NW>(p.xs, ix, x);
+                        load_gf_entry<NW>(p.ys, line, y);
+                        if (p.family == FAMILY_JULIA) {
+                            load_gf_entry<NW>(p.jc, 0, cx);
+                            load_gf_entry<NW>(p.jc, 1, cy);
+                        } else { cx = x; cy = y; }
+                        gf_pixel_init<NW>(st, x, y, cx, cy, cre_m, cim_m);
+                        active = true;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+        for (int k = 0; k < p.chunk; ++k) {
+            if (active) {
+                const bool esc = gf_pixel_step<NW>(st, cre_m, cim_m, scr, abs_im, abs_re);
+                if (esc || st.iter >= p.depth) {
+                    p.raw[pix] = esc ? st.iter : 0;
+                    __threadfence();
+                    active = false;
+                    const unsigned band = (pix / (unsigned)p.width) / (unsigned)p.aa;
+                    const unsigned done = atomicAdd(&p.band_count[band], 1u) + 1u;
+                    if (done == (unsigned)p.width * (unsigned)p.aa) finished_band = (int)band;
+                }
+            }
             if (publish_bands(p, finished_band, lane)) finished_band = -1;
             if (!__any_sync(0xffffffffu, active)) break;
         }

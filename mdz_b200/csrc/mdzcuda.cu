@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 #include <thread>
+#include <mutex>
+#include <map>
 
 #include "../../include/mdzcuda.h"
 #include "escape_kernel.cuh"
@@ -170,14 +172,31 @@ template <int N> static kernel_fn kfn() { return escape_mpfr_kernel<N>; }
 
 template <int NL> static kernel_fn gfn() { return escape_gmp_kernel<NL>; }
 
-// GMP mode: nl = P+1 64-bit limbs, P = mpf_init2's precision in limbs
+template <int NW> static kernel_fn gffn() { return escape_gmpf_kernel<NW>; }
+
+// GMP mode: nl = P+1 64-bit limbs, P = mpf_init2's precision in limbs.  The fast kernel
+// (mpf_fast.cuh) covers P >= 3; P = 2 (precision below 65 bits, which MDZ's settings
+// cannot select: image_info.c:535 keeps precision >= 80) uses the clear version.
 static kernel_fn gmp_kernel_for_limbs(int nl)
 {
+    if (!getenv("MDZCUDA_GMP_CLEAR")) {
+        switch (nl) {
+        case 4: return gffn<8>();   case 5: return gffn<10>();  case 6: return gffn<12>();  case 7: return gffn<14>();
+        case 8: return gffn<16>();  case 9: return gffn<18>();  case 10: return gffn<20>();
+        default: break;
+        }
+    }
     switch (nl) {
     case 3: return gfn<3>();  case 4: return gfn<4>();  case 5: return gfn<5>();  case 6: return gfn<6>();
     case 7: return gfn<7>();  case 8: return gfn<8>();  case 9: return gfn<9>();  case 10: return gfn<10>();
     default: return nullptr;
     }
+}
+
+static int gmp_smem_words(int nl)
+{
+    if (getenv("MDZCUDA_GMP_CLEAR") || nl < 4) return 0;
+    return 5 * 2 * nl;          // GSmemWords<2*nl>: c_re, c_im, 3-part shifter column
 }
 
 static int smem_words_for_limbs(int n)
@@ -400,24 +419,38 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
         CUDA_OKP(cudaEventCreateWithFlags(&pl->done_ev, cudaEventDisableTiming));
         pl->h_pinned = (unsigned int*)calloc(4, sizeof(unsigned int));   // tiny staging words (pageable: cudaMallocHost costs ~1 ms)
 
-        cudaFuncAttributes fa;
-        CUDA_OKP(cudaFuncGetAttributes(&fa, (const void*)fn));
-        cudaDeviceProp prop;
-        CUDA_OKP(cudaGetDeviceProperties(&prop, device));
-        const int smem = gmp ? 0 : smem_words_for_limbs(n32) * kBlock * (int)sizeof(uint32_t);   // c_re, c_im, shifter scratch, checkpoint
-        if (smem > 48 * 1024)
-            CUDA_OKP(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int occ = 0;
-        CUDA_OKP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, kBlock, smem));
-        if (occ < 1) { set_err("kernel for %d limbs does not fit on an SM", n32); goto fail; }
-        pl->info.limbs = n32;
-        pl->info.regs_per_thread = fa.numRegs;
-        pl->info.local_bytes = (int)fa.localSizeBytes;
-        pl->info.shared_bytes = smem;
-        pl->info.block_threads = kBlock;
-        pl->info.blocks_per_sm = occ;
-        pl->info.sm_count = prop.multiProcessorCount;
-        pl->info.grid_blocks = occ * prop.multiProcessorCount;
+        // kernel facts per (device, kernel) are cached: cudaGetDeviceProperties and the
+        // occupancy query cost milliseconds, which is a visible share of a 60 ms render
+        const int smem = (gmp ? gmp_smem_words(n32 / 2) : smem_words_for_limbs(n32)) * kBlock * (int)sizeof(uint32_t);   // c_re, c_im, shifter scratch, checkpoint
+        {
+            static std::mutex mu;
+            static std::map<std::pair<int, const void*>, mdzcuda_kernel_info> cache;
+            std::lock_guard<std::mutex> lock(mu);
+            auto key = std::make_pair(device, (const void*)fn);
+            auto it = cache.find(key);
+            if (it == cache.end()) {
+                cudaFuncAttributes fa;
+                CUDA_OKP(cudaFuncGetAttributes(&fa, (const void*)fn));
+                int sms = 0;
+                CUDA_OKP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+                if (smem > 48 * 1024)
+                    CUDA_OKP(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                int occ = 0;
+                CUDA_OKP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, kBlock, smem));
+                if (occ < 1) { set_err("kernel for %d limbs does not fit on an SM", n32); goto fail; }
+                mdzcuda_kernel_info ki;
+                ki.limbs = n32;
+                ki.regs_per_thread = fa.numRegs;
+                ki.local_bytes = (int)fa.localSizeBytes;
+                ki.shared_bytes = smem;
+                ki.block_threads = kBlock;
+                ki.blocks_per_sm = occ;
+                ki.sm_count = sms;
+                ki.grid_blocks = occ * sms;
+                it = cache.insert(std::make_pair(key, ki)).first;
+            }
+            pl->info = it->second;
+        }
     }
     return pl;
 fail:

@@ -165,3 +165,82 @@ extern "C" long emu_gmp_pixel(int nl, int fractal, long depth,
     default: return -1;
     }
 }
+
+// ---- GMP mpf mode, fast register implementation (mpf_fast.cuh) -------------------------
+#include "../../mdz_b200/csrc/mpf_fast.cuh"
+
+template <int NL>
+static int gmpf_op(int op, const uint64_t* al, long ae, int as, const uint64_t* bl, long be, int bs,
+                   uint64_t* rl, long* re, int* rs)
+{
+    constexpr int NW = 2 * NL;
+    Mpf<NL> a, b, z;
+    for (int i = 0; i < NL; ++i) { a.l[i] = al[i]; b.l[i] = bl[i]; }
+    a.e = (int32_t)ae; a.s = as < 0; b.e = (int32_t)be; b.s = bs < 0;
+    if (as == 0) gset_zero(a);
+    if (bs == 0) gset_zero(b);
+    GF<NW> x, y, r;
+    gf_from_slow<NW>(a, x); gf_from_slow<NW>(b, y);
+    uint32_t scratch[GScratchWords<NW>::value] = {0};
+    switch (op) {
+    case 0: gf_mul<NW, false>(x, y, r); break;
+    case 1: gf_mul2<NW>(x, r); break;
+    case 2: gf_addsub<NW>(x, y, r, false, scratch); break;
+    case 3: gf_addsub<NW>(x, y, r, true, scratch); break;
+    case 4: *rs = gf_gt4<NW>(x) ? 1 : 0; return 1;
+    case 5: gf_mul<NW, true>(x, x, r); break;
+    default: return 0;
+    }
+    gf_to_slow<NW>(r, z);
+    for (int i = 0; i < NL; ++i) rl[i] = z.l[i];
+    *re = z.e; *rs = gz(z) ? 0 : (z.s ? -1 : 1);
+    return 1;
+}
+
+#define GFCASE(n) case n: return gmpf_op<n>(op, al, ae, as, bl, be, bs, rl, re, rs);
+extern "C" int emu_gmpf_op(int op, int nl, const uint64_t* al, long ae, int as,
+                           const uint64_t* bl, long be, int bs, uint64_t* rl, long* re, int* rs)
+{
+    switch (nl) {
+    GFCASE(4) GFCASE(5) GFCASE(6) GFCASE(7) GFCASE(8) GFCASE(9) GFCASE(10) GFCASE(11) GFCASE(12)
+    GFCASE(13) GFCASE(14) GFCASE(15) GFCASE(16) GFCASE(17) GFCASE(18)
+    default: return 0;
+    }
+}
+
+template <int NL>
+static long gmpf_pixel(int fractal, long depth, const uint64_t* const* l, const long* ex, const int* sg)
+{
+    constexpr int NW = 2 * NL;
+    GF<NW> v[4];
+    for (int k = 0; k < 4; ++k) {
+        Mpf<NL> t;
+        for (int i = 0; i < NL; ++i) t.l[i] = l[k][i];
+        t.e = (int32_t)ex[k]; t.s = sg[k] < 0;
+        if (sg[k] == 0) gset_zero(t);
+        gf_from_slow<NW>(t, v[k]);
+    }
+    uint32_t cre[NW], cim[NW], scratch[GScratchWords<NW>::value] = {0};
+    GFPixel<NW> st;
+    gf_pixel_init<NW>(st, v[0], v[1], v[2], v[3], cre, cim);
+    const bool abs_im = fractal == FRACTAL_BURNING_SHIP;
+    const int abs_re = fractal == FRACTAL_GENERALIZED_CELTIC ? 1 : fractal == FRACTAL_VARIANT ? 2 : 0;
+    while (st.iter < depth)
+        if (gf_pixel_step<NW>(st, cre, cim, scratch, abs_im, abs_re)) return st.iter;
+    return 0;
+}
+
+#define GFPCASE(n) case n: return gmpf_pixel<n>(fractal, depth, l, ex, sg);
+extern "C" long emu_gmpf_pixel(int nl, int fractal, long depth,
+                               const uint64_t* xl, long xe, int xs, const uint64_t* yl, long ye, int ys,
+                               const uint64_t* cxl, long cxe, int cxs, const uint64_t* cyl, long cye, int cys)
+{
+    const uint64_t* l[4] = {xl, yl, cxl, cyl};
+    const long ex[4] = {xe, ye, cxe, cye};
+    const int sg[4] = {xs, ys, cxs, cys};
+    switch (nl) {
+    GFPCASE(4) GFPCASE(5) GFPCASE(6) GFPCASE(7) GFPCASE(8) GFPCASE(9) GFPCASE(10) GFPCASE(11) GFPCASE(12)
+    GFPCASE(13) GFPCASE(14) GFPCASE(15) GFPCASE(16) GFPCASE(17) GFPCASE(18)
+    default: return -1;
+    }
+}

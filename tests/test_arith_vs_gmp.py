@@ -135,17 +135,19 @@ def rand_pair(rng, P):
 @pytest.fixture(scope="module")
 def emu(emu_lib):
     P64 = C.POINTER(U64)
-    emu_lib.emu_gmp_op.argtypes = [C.c_int, C.c_int, P64, C.c_long, C.c_int, P64, C.c_long, C.c_int,
-                                   P64, C.POINTER(C.c_long), C.POINTER(C.c_int)]
+    for fn in (emu_lib.emu_gmp_op, emu_lib.emu_gmpf_op):
+        fn.argtypes = [C.c_int, C.c_int, P64, C.c_long, C.c_int, P64, C.c_long, C.c_int,
+                       P64, C.POINTER(C.c_long), C.POINTER(C.c_int)]
     return emu_lib
 
 
-def emu_op(emu, op, a, b):
+def emu_op(emu, op, a, b, fast=False):
     nl = a.P + 1
     al, ae, as_ = a.fixed()
     bl, be, bs = b.fixed()
     rl, re_, rs = (U64 * nl)(), C.c_long(), C.c_int()
-    assert emu.emu_gmp_op(op, nl, (U64 * nl)(*al), ae, as_, (U64 * nl)(*bl), be, bs, rl, C.byref(re_), C.byref(rs))
+    fn = emu.emu_gmpf_op if fast else emu.emu_gmp_op
+    assert fn(op, nl, (U64 * nl)(*al), ae, as_, (U64 * nl)(*bl), be, bs, rl, C.byref(re_), C.byref(rs))
     if op == 4:
         return rs.value
     return canon(rs.value, re_.value, list(rl))
@@ -169,3 +171,76 @@ def test_ops_match_libgmp(emu, p):
         # compare against 4 on a small positive value
         c = G(P, 1, rng.choice([0, 1, 1, 1, 2]), [rng.choice([0, 1, rng.getrandbits(64)]), rng.choice([3, 4, 4, 5])])
         assert emu_op(emu, 4, c, c) == (1 if mpf_cmp(c.ref, four.ref) > 0 else 0)
+
+
+@pytest.mark.parametrize("p", [80, 128, 200, 256, 320, 512, 1024])
+def test_fast_ops_match_libgmp(emu, p):
+    """mpf_fast.cuh (the register / IMAD.WIDE implementation the kernel uses)."""
+    P = prec_limbs(p)
+    rng = random.Random(1700 + p)
+    four = G(P, 1, 1, [4])
+    for _ in range(6000):
+        a, b = rand_pair(rng, P)
+        r = G(P)
+        for op, fn in ((0, mpf_mul), (2, mpf_add), (3, mpf_sub)):
+            fn(r.ref, a.ref, b.ref)
+            assert emu_op(emu, op, a, b, True) == r.value(), (op, a.fixed(), b.fixed())
+        mpf_mul(r.ref, a.ref, a.ref)
+        assert emu_op(emu, 5, a, a, True) == r.value(), ("sqr", a.fixed())
+        mpf_mul_ui(r.ref, a.ref, 2)
+        assert emu_op(emu, 1, a, a, True) == r.value(), ("mul2", a.fixed())
+        c = G(P, 1, rng.choice([0, 1, 1, 1, 2]), [rng.choice([0, 1, rng.getrandbits(64)]), rng.choice([3, 4, 4, 5])])
+        assert emu_op(emu, 4, c, c, True) == (1 if mpf_cmp(c.ref, four.ref) > 0 else 0)
+
+
+@pytest.mark.parametrize("p", [80, 128, 320, 512])
+def test_fast_products_next_to_truncation_boundary(emu, p):
+    """gf_mul forms only the high columns of the product and falls back to the full
+    product when the guard word is within the truncation error of wrapping.  Build
+    operands whose exact product has that guard word a few units from 0xffffffff with
+    random words below, so the carry into the kept limbs really depends on what was
+    left out; and squares likewise (2-adic square roots)."""
+    from test_arith_vs_mpfr import _sqrt_mod_2k
+    P = prec_limbs(p)
+    M = 2 * P                      # 32-bit words of an operand
+    rng = random.Random(5100 + p)
+    k = 32 * (M - 4)               # product bits below position M-4
+    for trial in range(1500):
+        # The kept columns hold (true product - omitted part); the omitted part is worth up to
+        # ~M units of word M-6.  When the TRUE product has word M-5 == 0 and a tiny word M-6,
+        # the truncated sum borrows through both and the limbs above come out one short.
+        delta = rng.randrange(0, 3 * M + 8)
+        w5 = 0 if rng.randrange(4) else rng.choice([1, 0xFFFFFFFF, 0xFFFFFFFE])
+        low = rng.getrandbits(32 * (M - 6)) if rng.randrange(4) else 0
+        L = (w5 << (32 * (M - 5))) | (delta << (32 * (M - 6))) | low
+        if trial % 3 == 0:
+            L = (L & ~7) | 1
+            a = _sqrt_mod_2k(L % (1 << k), k)
+            a |= rng.getrandbits(32 * 4) << k
+            b = a
+        else:
+            a = rng.getrandbits(32 * M) | 1
+            b = (L * pow(a, -1, 1 << k)) % (1 << k)
+            b |= rng.getrandbits(32 * 4) << k
+        # small top limbs make the product's top limb zero (GMP drops it: the kept window
+        # then reaches two words further down, right next to the guard word)
+        topmask = (1 << (64 * (P - 1))) - 1
+        if P >= 4 and rng.randrange(3):
+            a = (a & topmask) | (rng.randrange(1, 1 << 20) << (64 * (P - 1)))
+            b = (b & topmask) | (rng.randrange(1, 1 << 20) << (64 * (P - 1)))
+        if a >> (64 * (P - 1)) == 0:
+            a |= 1 << (64 * P - 7)
+        if b >> (64 * (P - 1)) == 0:
+            b |= 1 << (64 * P - 7)
+        if trial % 3 == 0:
+            b = a
+        def limbs(v):
+            return [rng.getrandbits(64)] + [(v >> (64 * i)) & M64 for i in range(P)]
+        A = G(P, 1, rng.randrange(-2, 3), limbs(a))
+        B = A if trial % 3 == 0 else G(P, rng.choice([1, -1]), rng.randrange(-2, 3), limbs(b))
+        r = G(P)
+        mpf_mul(r.ref, A.ref, B.ref)
+        if trial % 3 == 0:
+            assert emu_op(emu, 5, A, A, True) == r.value(), hex(a)
+        else:
+            assert emu_op(emu, 0, A, B, True) == r.value(), (hex(a), hex(b))

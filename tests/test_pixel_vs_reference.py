@@ -142,10 +142,12 @@ GCASES = [
 ]
 
 
+@pytest.mark.parametrize("impl", ["emu_gmp_pixel", "emu_gmpf_pixel"], ids=["clear", "fast"])
 @pytest.mark.parametrize("name,mk,count", GCASES, ids=[c[0] for c in GCASES])
-def test_gmp_pixels_match_reference(emu_lib, ref_lib, name, mk, count):
-    emu_lib.emu_gmp_pixel.restype = C.c_long
-    emu_lib.emu_gmp_pixel.argtypes = [C.c_int, C.c_int, C.c_long] + [U, C.c_long, C.c_int] * 4
+def test_gmp_pixels_match_reference(emu_lib, ref_lib, name, mk, count, impl):
+    fn = getattr(emu_lib, impl)
+    fn.restype = C.c_long
+    fn.argtypes = [C.c_int, C.c_int, C.c_long] + [U, C.c_long, C.c_int] * 4
     view = mk()
     nl = (max(53, view.precision) + 127) // 64 + 1
     W, H = view.real_width, view.real_height
@@ -155,5 +157,5 @@ def test_gmp_pixels_match_reference(emu_lib, ref_lib, name, mk, count):
         args = []
         for v in (x, y, x, y):
             args += list(fixed_mpf(v, nl))
-        got = emu_lib.emu_gmp_pixel(nl, view.fractal, view.depth, *args)
+        got = fn(nl, view.fractal, view.depth, *args)
         assert got == gmp_ref_pixel(ref_lib, view, x, y), (name, ix, line)
