@@ -103,7 +103,7 @@ __device__ __forceinline__ void colour_band(const int* raw, int width, int aa, i
 }
 
 // recolour-only kernel (palette cycling from resident raw_data): one warp per band
-__global__ void recolour_kernel(const int* raw, int width, int aa, int bands, ColourParams cp)
+static __global__ void recolour_kernel(const int* raw, int width, int aa, int bands, ColourParams cp)
 {
     const unsigned lane = threadIdx.x & 31u;
     const int warps_per_block = blockDim.x >> 5;

@@ -15,6 +15,7 @@
 // Every `chunk` iterations a warp refills its finished lanes with one
 // warp-aggregated atomicAdd.
 #pragma once
+#include "escape_params.cuh"
 #include "escape_step.cuh"
 #include "mpf_sf.cuh"
 #include "mpf_fast.cuh"
@@ -22,40 +23,6 @@
 
 namespace mdz {
 
-// Column / row tables, limb-major so that lanes on neighbouring pixels coalesce.
-//   m[k * count + i]  limb k (0 = least significant) of entry i
-//   e[i]              exponent (E_ZERO for zero)
-//   s[i]              1 = negative
-struct CoordTable {
-    const uint32_t* m;
-    const int32_t*  e;
-    const uint32_t* s;
-    int count;
-};
-
-struct EscapeParams {
-    CoordTable xs;          // real_width entries: x[ix]      (fractal.c:183-186)
-    CoordTable ys;          // one entry per local line: y[line] (fractal.c:167-170)
-    CoordTable jc;          // 2 entries: julia c_re, c_im    (fractal.c:197-198)
-    RoundCfg rc;
-    int32_t* raw;           // [local_lines][width] iteration counts
-    unsigned int* queue;    // next pixel index
-    unsigned int* band_count;   // finished supersamples per band of aa lines
-    volatile unsigned int* bands_done;   // number of completed bands
-    unsigned char* band_flag;   // 1 when band complete (device copy, host polls a mirror)
-    const volatile int* cancel; // device stop flag, set by the host from a side stream (rth_ui_stop_render)
-    int width;              // real width
-    int lines;              // local line count (multiple of aa)
-    int aa;
-    int depth;
-    int family;
-    int fractal;
-    int chunk;              // iterations between refills
-    int spec;               // 1: try the speculative branch-free iteration first
-    ColourParams colour;    // fused epilogue: colour a band as soon as it completes (enabled = 0: raw only)
-};
-
-constexpr int kBlock = 128;
 
 // Warp-level completion of bands: every lane passes the band it just completed (or
 // -1).  All writers fenced before bumping the band counter, so after this fence the
@@ -92,9 +59,9 @@ __device__ __forceinline__ void load_entry(const CoordTable& t, int i, Num<N>& v
 
 // limb counts for which the speculative iteration (escape_step.cuh) is compiled in:
 // it keeps the previous state alive for the fall-back, 4N extra registers
-template <int N> struct SpecLimbs { static constexpr bool value = N >= 3; };
+template <int N> struct SpecLimbs { static constexpr bool value = N >= 3 && N <= 16; };
 // ... and from where on its checkpoint lives in shared memory instead of registers
-template <int N> struct SpecSmemCkpt { static constexpr bool value = N > 10; };
+template <int N> struct SpecSmemCkpt { static constexpr bool value = N > 10 && SpecLimbs<N>::value; };
 // shared-memory words per thread: c_re, c_im, limb-shifter scratch, checkpoint
 template <int N> struct SmemWords {
     static constexpr int value = 2 * N + ScratchWords<N>::value + (SpecSmemCkpt<N>::value ? CkptWords<N>::value : 0);
@@ -102,7 +69,7 @@ template <int N> struct SmemWords {
 
 // resident blocks per SM the register allocator is asked to make room for
 template <int N> struct MinBlocks {
-    static constexpr int value = N <= 3 ? 8 : N <= 5 ? 6 : N <= 8 ? 5 : N <= 12 ? 4 : 3;
+    static constexpr int value = N <= 3 ? 8 : N <= 5 ? 6 : N <= 8 ? 5 : N <= 12 ? 4 : N <= 16 ? 3 : N <= 24 ? 2 : 1;
 };
 
 template <int N>

@@ -18,7 +18,7 @@
 #include <map>
 
 #include "../../include/mdzcuda.h"
-#include "escape_kernel.cuh"
+#include "escape_params.cuh"
 #include "mp_convert.h"
 
 using namespace mdz;
@@ -168,60 +168,30 @@ struct mdzcuda_plan {
 
 typedef void (*kernel_fn)(const EscapeParams);
 
-template <int N> static kernel_fn kfn() { return escape_mpfr_kernel<N>; }
-
-template <int NL> static kernel_fn gfn() { return escape_gmp_kernel<NL>; }
-
-template <int NW> static kernel_fn gffn() { return escape_gmpf_kernel<NW>; }
+// The kernels are instantiated in separate translation units (kernels_*.cu) so that the
+// build parallelises: one unrolled kernel per limb count is seconds to minutes of ptxas.
+kernel_fn mdz_kernel_mpfr(int n32);             // N = 2..32 words   (kernels_mpfr_*.cu)
+int       mdz_smem_words_mpfr(int n32);
+kernel_fn mdz_kernel_gmp_clear(int nl);         // NL = 3..10 limbs  (kernels_gmp.cu)
+kernel_fn mdz_kernel_gmp_fast(int nl);          // NL = 4..10 limbs  (kernels_gmpf_*.cu)
+int       mdz_smem_words_gmp_fast(int nl);
 
 // GMP mode: nl = P+1 64-bit limbs, P = mpf_init2's precision in limbs.  The fast kernel
 // (mpf_fast.cuh) covers P >= 3; P = 2 (precision below 65 bits, which MDZ's settings
-// cannot select: image_info.c:535 keeps precision >= 80) uses the clear version.
+// cannot select: image_info.c:535 keeps precision >= 80) uses the clear version, as does
+// everything when MDZCUDA_GMP_CLEAR is set (A/B measurements).
 static kernel_fn gmp_kernel_for_limbs(int nl)
 {
-    if (!getenv("MDZCUDA_GMP_CLEAR")) {
-        switch (nl) {
-        case 4: return gffn<8>();   case 5: return gffn<10>();  case 6: return gffn<12>();  case 7: return gffn<14>();
-        case 8: return gffn<16>();  case 9: return gffn<18>();  case 10: return gffn<20>();
-        default: break;
-        }
-    }
-    switch (nl) {
-    case 3: return gfn<3>();  case 4: return gfn<4>();  case 5: return gfn<5>();  case 6: return gfn<6>();
-    case 7: return gfn<7>();  case 8: return gfn<8>();  case 9: return gfn<9>();  case 10: return gfn<10>();
-    default: return nullptr;
-    }
+    if (!getenv("MDZCUDA_GMP_CLEAR")) { kernel_fn f = mdz_kernel_gmp_fast(nl); if (f) return f; }
+    return mdz_kernel_gmp_clear(nl);
 }
-
 static int gmp_smem_words(int nl)
 {
-    if (getenv("MDZCUDA_GMP_CLEAR") || nl < 4) return 0;
-    return 5 * 2 * nl;          // GSmemWords<2*nl>: c_re, c_im, 3-part shifter column
+    if (getenv("MDZCUDA_GMP_CLEAR")) return 0;
+    return mdz_smem_words_gmp_fast(nl);
 }
-
-static int smem_words_for_limbs(int n)
-{
-    switch (n) {
-    case 2: return SmemWords<2>::value;   case 3: return SmemWords<3>::value;   case 4: return SmemWords<4>::value;
-    case 5: return SmemWords<5>::value;   case 6: return SmemWords<6>::value;   case 7: return SmemWords<7>::value;
-    case 8: return SmemWords<8>::value;   case 9: return SmemWords<9>::value;   case 10: return SmemWords<10>::value;
-    case 11: return SmemWords<11>::value; case 12: return SmemWords<12>::value; case 13: return SmemWords<13>::value;
-    case 14: return SmemWords<14>::value; case 15: return SmemWords<15>::value; case 16: return SmemWords<16>::value;
-    default: return 0;
-    }
-}
-
-static kernel_fn kernel_for_limbs(int n)
-{
-    switch (n) {
-    case 2: return kfn<2>();   case 3: return kfn<3>();   case 4: return kfn<4>();
-    case 5: return kfn<5>();   case 6: return kfn<6>();   case 7: return kfn<7>();
-    case 8: return kfn<8>();   case 9: return kfn<9>();   case 10: return kfn<10>();
-    case 11: return kfn<11>(); case 12: return kfn<12>(); case 13: return kfn<13>();
-    case 14: return kfn<14>(); case 15: return kfn<15>(); case 16: return kfn<16>();
-    default: return nullptr;
-    }
-}
+static kernel_fn kernel_for_limbs(int n) { return mdz_kernel_mpfr(n); }
+static int smem_words_for_limbs(int n) { return mdz_smem_words_mpfr(n); }
 
 // ---- prologue: MPFR mode (reference src/fractal.c:143-188) ------------------
 static int prologue_mpfr(const mdzcuda_view* v, const std::vector<int>& lines,

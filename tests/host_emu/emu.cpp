@@ -47,7 +47,8 @@ extern "C" int emu_binop(int op, long prec,
 {
     switch (limbs32_for_prec(prec)) {
     CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
-    CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16) CASE(20) CASE(24) CASE(32)
+    CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16) CASE(17) CASE(18) CASE(19) CASE(20) CASE(21)
+    CASE(22) CASE(23) CASE(24) CASE(25) CASE(26) CASE(27) CASE(28) CASE(29) CASE(30) CASE(31) CASE(32)
     default: return 0;
     }
 }
@@ -87,7 +88,8 @@ extern "C" long emu_pixel(long prec, int fractal, long depth, int spec,
     const long ex[4] = {xe, ye, cxe, cye};
     switch (limbs32_for_prec(prec)) {
     PCASE(2) PCASE(3) PCASE(4) PCASE(5) PCASE(6) PCASE(7) PCASE(8) PCASE(9) PCASE(10)
-    PCASE(11) PCASE(12) PCASE(13) PCASE(14) PCASE(15) PCASE(16) PCASE(20) PCASE(24) PCASE(32)
+    PCASE(11) PCASE(12) PCASE(13) PCASE(14) PCASE(15) PCASE(16) PCASE(17) PCASE(18) PCASE(19) PCASE(20) PCASE(21)
+    PCASE(22) PCASE(23) PCASE(24) PCASE(25) PCASE(26) PCASE(27) PCASE(28) PCASE(29) PCASE(30) PCASE(31) PCASE(32)
     default: return -1;
     }
 }

@@ -12,7 +12,7 @@ import pytest
 from mdz_b200.mp import Mpfr, mpfr, nlimbs64
 
 U64P = C.POINTER(C.c_uint64)
-PRECS = [64, 65, 80, 95, 96, 97, 113, 128, 176, 184, 256, 320, 511, 512]
+PRECS = [64, 65, 80, 95, 96, 97, 113, 128, 176, 184, 256, 320, 511, 512, 544, 640, 777, 1000, 1024]
 
 
 def rand_mant(rng, prec):

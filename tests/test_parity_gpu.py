@@ -31,7 +31,7 @@ def test_long_double_fractals(ref_lib, fractal):
     check(make_view("-0.5", "-0.3", "3.5", 160, 120, mode="ld", depth=500, fractal=fractal), ref_lib)
 
 
-@pytest.mark.parametrize("prec", [80, 96, 128, 176, 184, 256, 320, 512])
+@pytest.mark.parametrize("prec", [80, 96, 128, 176, 184, 256, 320, 512, 544, 640, 800, 1024])
 def test_mpfr_precisions_seahorse(ref_lib, prec):
     check(make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", 96, 72, precision=prec, depth=1500), ref_lib)
 
