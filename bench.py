@@ -271,14 +271,20 @@ def main():
 
     # ---- end-to-end through the public call: host view in, host raw_data out ----
     xs_bytes = (plan.kernel_info()["limbs"] + 2) * 4 * (view.real_width + plan.local_lines() + 2)
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 20))
+    out = np.empty((view.real_height, view.real_width), dtype=np.int32)   # the caller's raw_data (pageable, as MDZ's malloc)
+    out.fill(-1)
+    for _ in range(2):                                                          # untimed: pool warm, pages touched
+        p2 = mdz_b200.Plan(view, local, band_first=rank, band_stride=world); p2.run(out, stream); p2.close()
     barrier()
+    e2e_ms = []
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        p2 = mdz_b200.Plan(view, local, band_first=rank, band_stride=world)   # prologue + H2D
-        p2.launch(stream)
-        out = p2.fetch()                                                         # sync + D2H
+        ta = time.perf_counter()
+        p2 = mdz_b200.Plan(view, local, band_first=rank, band_stride=world)   # prologue + H2D of the tables
+        p2.run(out, stream)                                                      # kernel; bands D2H as they complete
         p2.close()
+        e2e_ms.append(round((time.perf_counter() - ta) * 1e3, 3))
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -309,7 +315,9 @@ def main():
                        "l2": "256 MiB buffer rewritten between steps (inputs are KB-sized tables)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps,
                     "h2d_bytes_per_step": xs_bytes, "d2h_bytes_per_step": int(my_lines.nbytes),
-                    "includes": "host prologue (libmpfr/long double tables), H2D, kernel, D2H of raw_data"},
+                    "ms_each": e2e_ms,
+                    "includes": "mdzcuda_plan_create (host prologue with libmpfr/long double, H2D of the tables) + "
+                                "mdzcuda_plan_run (kernel, D2H of finished bands into pageable host raw_data) + destroy"},
             "gpu_launches": args.steps * world,
             "clocks": clocks,
             "roofline": {"bound": "imad", "achieved": kernel_rate * macs / 1e12, "peak": peak / 1e12,

@@ -157,7 +157,19 @@ typedef struct mdzcuda_kernel_info {
 } mdzcuda_kernel_info;
 int mdzcuda_plan_kernel_info(mdzcuda_plan*, mdzcuda_kernel_info* out);
 
+/* Launch on `cuda_stream` and deliver: finished bands are copied into the full-size
+ * host raw_data array while the kernel is still running, so the call returns shortly
+ * after the last pixel.  Equivalent to launch + fetch. */
+int mdzcuda_plan_run(mdzcuda_plan*, void* cuda_stream, int32_t* raw_host);
+
+/* Returns the plan's device buffers, side stream and event to a per-device pool that
+ * the next plan draws from (MDZ re-renders on every mouse move in its Julia preview,
+ * src/main_gui.c:786-793; cudaMalloc/cudaFree per render cost milliseconds). */
 void mdzcuda_plan_destroy(mdzcuda_plan*);
+
+/* Give the pooled device memory (at most MDZCUDA_POOL_MB, default 4096), streams
+ * and events back to the driver. */
+void mdzcuda_trim(void);
 
 /*
  * One-call render: host view in, host raw_data out, over ndev devices

@@ -63,7 +63,9 @@ SYMBOLS = {
     "mdzcuda_plan_device_raw": (C.c_void_p, [C.c_void_p]),
     "mdzcuda_plan_local_lines": (C.c_int, [C.c_void_p]),
     "mdzcuda_plan_kernel_info": (C.c_int, [C.c_void_p, C.POINTER(KernelInfo)]),
+    "mdzcuda_plan_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mdzcuda_plan_destroy": (None, [C.c_void_p]),
+    "mdzcuda_trim": (None, []),
     "mdzcuda_render": (C.c_int, [C.POINTER(View), C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "mdzcuda_imad_peak": (C.c_double, [C.c_int, C.c_int]),
     "mdzcuda_imad32_peak": (C.c_double, [C.c_int, C.c_int]),

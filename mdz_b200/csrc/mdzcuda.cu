@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <time.h>
 #include <float.h>
 #include <string>
 #include <vector>
@@ -46,6 +47,161 @@ extern "C" int mdzcuda_device_count(void)
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess) { set_err("cudaGetDeviceCount: %s", cudaGetErrorString(e)); return 0; }
     return n;
+}
+
+// ---------------------------------------------------------------------------
+// Device memory / stream / event pool.
+//
+// A render is 60 ms of kernel; cudaMalloc + cudaFree of its buffers (and the
+// implicit device synchronisation of cudaFree) cost between 1 and tens of
+// milliseconds per call and vary from box to box.  MDZ re-renders constantly (the
+// Julia preview on every mouse move, main_gui.c:786-793), so freed blocks, side
+// streams, events and pinned staging words are kept per device and handed to the
+// next plan.  mdzcuda_trim() gives everything back to the driver.
+// ---------------------------------------------------------------------------
+namespace {
+struct DevPool {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks;       // capacity -> block
+    std::map<void*, size_t> live;                   // blocks handed out -> capacity
+    size_t cached = 0;
+    std::vector<cudaStream_t> streams;
+    std::vector<cudaEvent_t> events;
+    std::vector<unsigned int*> pinned;              // 16-word pinned staging chunks
+};
+constexpr int kMaxDev = 64;
+DevPool g_pool[kMaxDev];
+
+size_t pool_limit_bytes()
+{
+    static size_t lim = [] {
+        const char* e = getenv("MDZCUDA_POOL_MB");
+        return (size_t)(e && *e ? strtoull(e, nullptr, 10) : 4096) << 20;
+    }();
+    return lim;
+}
+
+size_t pool_round(size_t bytes)
+{
+    const size_t g = bytes <= (1u << 20) ? (64u << 10) : (2u << 20);
+    return (bytes + g - 1) / g * g;
+}
+
+// the current device must be `dev`
+cudaError_t pool_alloc(int dev, void** out, size_t bytes)
+{
+    DevPool& P = g_pool[dev];
+    const size_t want = pool_round(bytes ? bytes : 1);
+    {
+        std::lock_guard<std::mutex> lock(P.mu);
+        auto it = P.free_blocks.lower_bound(want);
+        if (it != P.free_blocks.end() && it->first <= 2 * want) {
+            *out = it->second;
+            P.live[it->second] = it->first;
+            P.cached -= it->first;
+            P.free_blocks.erase(it);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(out, want);
+    if (e != cudaSuccess) {                           // give the cache back and retry once
+        std::vector<void*> drop;
+        {
+            std::lock_guard<std::mutex> lock(P.mu);
+            for (auto& kv : P.free_blocks) drop.push_back(kv.second);
+            P.free_blocks.clear(); P.cached = 0;
+        }
+        for (void* q : drop) cudaFree(q);
+        (void)cudaGetLastError();
+        e = cudaMalloc(out, want);
+        if (e != cudaSuccess) return e;
+    }
+    std::lock_guard<std::mutex> lock(P.mu);
+    P.live[*out] = want;
+    return cudaSuccess;
+}
+
+// the caller guarantees no work that touches the block is still in flight
+void pool_free(int dev, void* ptr)
+{
+    if (!ptr) return;
+    DevPool& P = g_pool[dev];
+    size_t cap = 0;
+    std::vector<void*> drop;
+    {
+        std::lock_guard<std::mutex> lock(P.mu);
+        auto it = P.live.find(ptr);
+        if (it == P.live.end()) { drop.push_back(ptr); }
+        else {
+            cap = it->second;
+            P.live.erase(it);
+            if (cap > pool_limit_bytes()) drop.push_back(ptr);
+            else {
+                P.free_blocks.insert(std::make_pair(cap, ptr));
+                P.cached += cap;
+                while (P.cached > pool_limit_bytes() && !P.free_blocks.empty()) {
+                    auto big = std::prev(P.free_blocks.end());
+                    P.cached -= big->first;
+                    drop.push_back(big->second);
+                    P.free_blocks.erase(big);
+                }
+            }
+        }
+    }
+    for (void* q : drop) cudaFree(q);
+}
+
+cudaError_t pool_stream(int dev, cudaStream_t* out)
+{
+    DevPool& P = g_pool[dev];
+    {
+        std::lock_guard<std::mutex> lock(P.mu);
+        if (!P.streams.empty()) { *out = P.streams.back(); P.streams.pop_back(); return cudaSuccess; }
+    }
+    return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking);
+}
+cudaError_t pool_event(int dev, cudaEvent_t* out)
+{
+    DevPool& P = g_pool[dev];
+    {
+        std::lock_guard<std::mutex> lock(P.mu);
+        if (!P.events.empty()) { *out = P.events.back(); P.events.pop_back(); return cudaSuccess; }
+    }
+    return cudaEventCreateWithFlags(out, cudaEventDisableTiming);
+}
+cudaError_t pool_pinned(int dev, unsigned int** out)
+{
+    DevPool& P = g_pool[dev];
+    {
+        std::lock_guard<std::mutex> lock(P.mu);
+        if (!P.pinned.empty()) { *out = P.pinned.back(); P.pinned.pop_back(); memset(*out, 0, 64); return cudaSuccess; }
+    }
+    cudaError_t e = cudaMallocHost((void**)out, 64);
+    if (e == cudaSuccess) memset(*out, 0, 64);
+    return e;
+}
+}  // namespace
+
+extern "C" void mdzcuda_trim(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return;
+    for (int dev = 0; dev < n && dev < kMaxDev; ++dev) {
+        DevPool& P = g_pool[dev];
+        std::vector<void*> drop; std::vector<cudaStream_t> ss; std::vector<cudaEvent_t> es; std::vector<unsigned int*> ps;
+        {
+            std::lock_guard<std::mutex> lock(P.mu);
+            for (auto& kv : P.free_blocks) drop.push_back(kv.second);
+            P.free_blocks.clear(); P.cached = 0;
+            ss.swap(P.streams); es.swap(P.events); ps.swap(P.pinned);
+        }
+        if (drop.empty() && ss.empty() && es.empty() && ps.empty()) continue;
+        if (cudaSetDevice(dev) != cudaSuccess) continue;
+        for (void* q : drop) cudaFree(q);
+        for (auto s : ss) cudaStreamDestroy(s);
+        for (auto e : es) cudaEventDestroy(e);
+        for (auto q : ps) cudaFreeHost(q);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -371,9 +527,9 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
             const size_t o_ctrl = ar.reserve(4);
             const size_t o_count = ar.reserve((size_t)pl->nbands + 1);
             const size_t o_flag = ar.reserve(((size_t)pl->nbands + 4) / 4 + 1);
-            CUDA_OKP(cudaMalloc(&pl->d_arena, ar.words * sizeof(uint32_t)));
+            CUDA_OKP(pool_alloc(device, (void**)&pl->d_arena, ar.words * sizeof(uint32_t)));
             CUDA_OKP(cudaMemcpy(pl->d_arena, ar.host.data(), table_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
-            CUDA_OKP(cudaMemset(pl->d_arena + o_ctrl, 0, (ar.words - o_ctrl) * sizeof(uint32_t)));
+            CUDA_OKP(cudaMemset(pl->d_arena + o_ctrl, 0, (ar.words - o_ctrl) * sizeof(uint32_t)));   // (the launch resets it again, in stream order)
             uint32_t* b = pl->d_arena;
             pl->xs.m = b + o[0]; pl->xs.e = (int32_t*)(b + o[1]); pl->xs.s = b + o[2]; pl->xs.count = xs.count;
             pl->ys.m = b + o[3]; pl->ys.e = (int32_t*)(b + o[4]); pl->ys.s = b + o[5]; pl->ys.count = ys.count;
@@ -384,10 +540,10 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
             pl->reset_words = ar.words - o_ctrl;
         }
         size_t npx = (size_t)pl->local_lines * v->real_width;
-        CUDA_OKP(cudaMalloc(&pl->d_raw, (npx ? npx : 1) * sizeof(int32_t)));
-        CUDA_OKP(cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking));
-        CUDA_OKP(cudaEventCreateWithFlags(&pl->done_ev, cudaEventDisableTiming));
-        pl->h_pinned = (unsigned int*)calloc(4, sizeof(unsigned int));   // tiny staging words (pageable: cudaMallocHost costs ~1 ms)
+        CUDA_OKP(pool_alloc(device, (void**)&pl->d_raw, (npx ? npx : 1) * sizeof(int32_t)));
+        CUDA_OKP(pool_stream(device, &pl->side));
+        CUDA_OKP(pool_event(device, &pl->done_ev));
+        CUDA_OKP(pool_pinned(device, &pl->h_pinned));                    // staging words for progress / cancel traffic
 
         // kernel facts per (device, kernel) are cached: cudaGetDeviceProperties and the
         // occupancy query cost milliseconds, which is a visible share of a 60 ms render
@@ -571,8 +727,8 @@ extern "C" int mdzcuda_plan_set_colour(mdzcuda_plan* pl, const mdzcuda_colour* c
     if (!c->palette || c->pal_indexes < 2 || c->pal_indexes > 256) { set_err("palette needs 2..256 entries"); return 0; }
     CUDA_OK(cudaSetDevice(pl->device));
     const int uw = pl->view.real_width / pl->view.aa_factor;
-    if (!pl->d_palette) CUDA_OK(cudaMalloc(&pl->d_palette, 256 * sizeof(uint32_t)));
-    if (!pl->d_rgb) CUDA_OK(cudaMalloc(&pl->d_rgb, ((size_t)pl->nbands * uw + 1) * sizeof(uint32_t)));
+    if (!pl->d_palette) CUDA_OK(pool_alloc(pl->device, (void**)&pl->d_palette, 256 * sizeof(uint32_t)));
+    if (!pl->d_rgb) CUDA_OK(pool_alloc(pl->device, (void**)&pl->d_rgb, ((size_t)pl->nbands * uw + 1) * sizeof(uint32_t)));
     CUDA_OK(cudaMemcpy(pl->d_palette, c->palette, (size_t)c->pal_indexes * sizeof(uint32_t), cudaMemcpyHostToDevice));
     pl->colour.palette = pl->d_palette;
     pl->colour.rgb = pl->d_rgb;
@@ -627,12 +783,76 @@ extern "C" void mdzcuda_plan_destroy(mdzcuda_plan* pl)
 {
     if (!pl) return;
     cudaSetDevice(pl->device);
-    cudaFree(pl->d_palette); cudaFree(pl->d_rgb);
-    cudaFree(pl->d_raw); cudaFree(pl->d_arena);
-    if (pl->side) cudaStreamDestroy(pl->side);
-    if (pl->done_ev) cudaEventDestroy(pl->done_ev);
-    free(pl->h_pinned);
+    // the blocks go back to the pool, so nothing of this plan may still be running
+    if (pl->done_ev) cudaEventSynchronize(pl->done_ev);
+    if (pl->side) cudaStreamSynchronize(pl->side);
+    DevPool& P = g_pool[pl->device];
+    pool_free(pl->device, pl->d_palette); pool_free(pl->device, pl->d_rgb);
+    pool_free(pl->device, pl->d_raw); pool_free(pl->device, pl->d_arena);
+    {
+        std::lock_guard<std::mutex> lock(P.mu);
+        if (pl->side) P.streams.push_back(pl->side);
+        if (pl->done_ev) P.events.push_back(pl->done_ev);
+        if (pl->h_pinned) P.pinned.push_back(pl->h_pinned);
+    }
     delete pl;
+}
+
+// Copy the bands of running plans into raw_host as they complete, so that by the time
+// the kernels end only the last few bands are still on the device (the D2H of an
+// 8 MB raw_data otherwise adds 2-3 ms to a 60 ms render).  Same mechanism the rth_*
+// layer uses to feed rth_process_lines_rendered, minus the publishing.
+static int deliver_bands(std::vector<mdzcuda_plan*>& plans, int32_t* raw_host)
+{
+    const int n = (int)plans.size();
+    std::vector<std::vector<unsigned char> > flags(n), seen(n);
+    std::vector<int> left(n, 0);
+    int remaining = 0;
+    for (int i = 0; i < n; ++i) {
+        const int nb = plans[i]->nbands;
+        flags[i].assign((size_t)nb + 1, 0); seen[i].assign((size_t)nb + 1, 0);
+        left[i] = nb; remaining += nb;
+    }
+    const struct timespec nap = { 0, 250 * 1000 };
+    while (remaining > 0) {
+        bool progress = false;
+        for (int i = 0; i < n; ++i) {
+            if (!left[i]) continue;
+            mdzcuda_plan* pl = plans[i];
+            const int nb = pl->nbands;
+            CUDA_OK(cudaSetDevice(pl->device));
+            const cudaError_t q = cudaEventQuery(pl->done_ev);
+            if (q != cudaSuccess && q != cudaErrorNotReady) { set_err("kernel failed: %s", cudaGetErrorString(q)); return 0; }
+            const bool finished = q == cudaSuccess;
+            if (finished) memset(flags[i].data(), 1, (size_t)nb);     // (a cancelled launch leaves its unfinished bands as they are)
+            else if (mdzcuda_plan_poll_bands(pl, flags[i].data()) < 0) return 0;
+            // whole runs only, and not in crumbs: each copy costs ~20 us of driver time
+            const int min_run = finished ? 1 : 16;
+            for (int b = 0; b < nb;) {
+                if (!flags[i][b] || seen[i][b]) { ++b; continue; }
+                int e = b;
+                while (e < nb && flags[i][e] && !seen[i][e]) ++e;
+                if (e - b >= min_run) {
+                    if (!mdzcuda_plan_fetch_bands(pl, raw_host, b, e - b)) return 0;
+                    for (int k = b; k < e; ++k) seen[i][k] = 1;
+                    left[i] -= e - b; remaining -= e - b;
+                    progress = true;
+                }
+                b = e;
+            }
+        }
+        if (!progress && remaining > 0) nanosleep(&nap, 0);
+    }
+    for (int i = 0; i < n; ++i) if (!mdzcuda_plan_wait(plans[i])) return 0;
+    return 1;
+}
+
+extern "C" int mdzcuda_plan_run(mdzcuda_plan* pl, void* cuda_stream, int32_t* raw_host)
+{
+    if (!pl || !raw_host) { set_err("null argument"); return 0; }
+    if (!mdzcuda_plan_launch(pl, cuda_stream)) return 0;
+    std::vector<mdzcuda_plan*> one(1, pl);
+    return deliver_bands(one, raw_host);
 }
 
 extern "C" int mdzcuda_render(const mdzcuda_view* view, int32_t* raw_host, int ndev, const int* devices)
@@ -641,18 +861,26 @@ extern "C" int mdzcuda_render(const mdzcuda_view* view, int32_t* raw_host, int n
     if (ndev < 1) ndev = 1;
     std::vector<mdzcuda_plan*> plans(ndev, nullptr);
     int ok = 1;
-    // plan creation runs the prologue; do it per device in parallel host threads
-    std::vector<std::thread> th;
-    std::vector<std::string> errs(ndev);
-    for (int i = 0; i < ndev; ++i)
-        th.emplace_back([&, i]() {
-            plans[i] = mdzcuda_plan_create(view, devices ? devices[i] : i, i, ndev);
-            if (!plans[i]) errs[i] = mdzcuda_last_error();
-        });
-    for (auto& t : th) t.join();
-    for (int i = 0; i < ndev; ++i) if (!plans[i]) { ok = 0; set_err("%s", errs[i].c_str()); }
+    if (ndev == 1) {
+        plans[0] = mdzcuda_plan_create(view, devices ? devices[0] : 0, 0, 1);
+        if (!plans[0]) ok = 0;
+    } else {
+        // plan creation runs the prologue; do it per device in parallel host threads
+        std::vector<std::thread> th;
+        std::vector<std::string> errs(ndev);
+        for (int i = 0; i < ndev; ++i)
+            th.emplace_back([&, i]() {
+                plans[i] = mdzcuda_plan_create(view, devices ? devices[i] : i, i, ndev);
+                if (!plans[i]) errs[i] = mdzcuda_last_error();
+            });
+        for (auto& t : th) t.join();
+        for (int i = 0; i < ndev; ++i) if (!plans[i]) { ok = 0; set_err("%s", errs[i].c_str()); }
+    }
     for (int i = 0; ok && i < ndev; ++i) ok = mdzcuda_plan_launch(plans[i], nullptr);
-    for (int i = 0; ok && i < ndev; ++i) ok = mdzcuda_plan_fetch(plans[i], raw_host);
+    if (ok) {
+        std::vector<mdzcuda_plan*> live(plans);
+        ok = deliver_bands(live, raw_host);
+    }
     std::string keep = g_err;
     for (int i = 0; i < ndev; ++i) mdzcuda_plan_destroy(plans[i]);
     g_err = keep;

@@ -140,6 +140,16 @@ class Plan:
         self._chk(_l.lib.mdzcuda_plan_fetch(self.h, out.ctypes.data_as(C.c_void_p)), "plan_fetch")
         return out
 
+    def run(self, out=None, stream=None):
+        """launch + deliver: bands are copied to `out` while the kernel runs."""
+        v = self.view
+        if out is None:
+            out = np.full((v.real_height, v.real_width), -1, dtype=np.int32)
+        assert out.dtype == np.int32 and out.flags["C_CONTIGUOUS"]
+        assert out.shape == (v.real_height, v.real_width)
+        self._chk(_l.lib.mdzcuda_plan_run(self.h, C.c_void_p(stream or 0), out.ctypes.data_as(C.c_void_p)), "plan_run")
+        return out
+
     def set_colour(self, palette, pal_offset=0, colour_scale=1.0, palette_ip=False):
         """Switch the fused colour epilogue on (palette: packed R|G<<8|B<<16 ints)."""
         pal = np.ascontiguousarray(np.asarray(palette, dtype=np.uint32))

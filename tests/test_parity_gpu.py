@@ -129,3 +129,32 @@ def test_gmp_deep_zoom_512(ref_lib):
     check_gmp(make_view(cx, "0.0281753397792110489924115211443195096875390767429906085704013095958801" 
                         "743240920186385400814658560553615695084486774077", "1e-120", 48, 27,
                         mode="gmp", precision=512, depth=3000), ref_lib)
+
+
+def test_plan_run_delivers_what_fetch_returns_and_pool_reuse(ref_lib):
+    """mdzcuda_plan_run (bands copied to the host while the kernel runs) against
+    launch + fetch and against the reference; plans created after a destroy draw their
+    buffers from the pool (stale contents must not leak into a result), also after
+    mdzcuda_trim, for strided bands and with several plans alive at once."""
+    from mdz_b200 import _native
+    v = config2(256, 144, 1500)
+    want, _ = ref_render(ref_lib, v)
+    for rep in range(4):
+        p = mdz_b200.Plan(v, 0)
+        got = p.run()
+        p.launch(); again = p.fetch()
+        p.close()
+        assert np.array_equal(got, want) and np.array_equal(again, want)
+        if rep == 1:
+            _native.lib.mdzcuda_trim()
+    # a different view of the same size right after: same pooled blocks, new contents
+    v2 = make_view("-0.1", "0.8", "0.5", 256, 144, mode="ld", depth=700)
+    want2, _ = ref_render(ref_lib, v2)
+    assert np.array_equal(mdz_b200.render(v2), want2)
+    plans = [mdz_b200.Plan(v2, 0, first, 3) for first in range(3)]
+    out = np.full_like(want2, -1)
+    for p in plans:
+        p.run(out)
+    for p in plans:
+        p.close()
+    assert np.array_equal(out, want2)
