@@ -17,6 +17,7 @@
 #pragma once
 #include "escape_params.cuh"
 #include "escape_step.cuh"
+#include "ld64_step.cuh"
 #include "mpf_sf.cuh"
 #include "mpf_fast.cuh"
 #include "colour.cuh"
@@ -59,7 +60,7 @@ __device__ __forceinline__ void load_entry(const CoordTable& t, int i, Num<N>& v
 
 // limb counts for which the speculative iteration (escape_step.cuh) is compiled in:
 // it keeps the previous state alive for the fall-back, 4N extra registers
-template <int N> struct SpecLimbs { static constexpr bool value = N >= 3 && N <= 16; };
+template <int N> struct SpecLimbs { static constexpr bool value = N >= 2 && N <= 16; };   // N = 2: ld64_step.cuh
 // ... and from where on its checkpoint lives in shared memory instead of registers
 template <int N> struct SpecSmemCkpt { static constexpr bool value = N > 10 && SpecLimbs<N>::value; };
 // shared-memory words per thread: c_re, c_im, limb-shifter scratch, checkpoint

@@ -1,0 +1,155 @@
+// ld64_step.cuh -- the escape-time iteration at p = 64 on a 64-bit significand:
+// the hardware ("long double") mode of the reference, src/frac_mandel.c:5-21,
+// src/frac_burning_ship.c:5-23, src/frac_generalized_celtic.c:5-23,
+// src/frac_variant.c:5-22, whose x87 arithmetic (64-bit significand, round to
+// nearest even) is the MPFR rule at precision 64 (SURVEY finding 1).
+//
+// This is the speculative step of escape_step.cuh specialised for two limbs.  The
+// generic limb code spends most of its instructions on cases a 64-bit significand
+// does not have (guard limbs, limb shifters, rounding positions inside a limb); here
+// a product is four IMAD.WIDE, a sum is formed exactly in a 128-bit frame (so rounding
+// needs no sticky bookkeeping), and round-to-nearest-even is one four-instruction
+// carry chain.  The whole iteration is one basic block.  Everything outside the
+// covered domain raises `rare`, and the caller (pixel_step_auto) redoes the iteration
+// with the general step, so results are those of the general code by construction:
+//   covered:  exponent gap of an addition <= 62, fewer than 64 cancelled bits,
+//             no zero / underflowed operand, no rounding carry out of the top bit.
+#pragma once
+#include "escape_step.cuh"
+
+namespace mdz {
+
+#if defined(MDZ_HOST_EMU)
+inline uint64_t shr64c(uint64_t x, uint32_t n) { return n >= 64 ? 0 : x >> n; }
+inline uint64_t shl64c(uint64_t x, uint32_t n) { return n >= 64 ? 0 : x << n; }
+// {m1:m0} = {h1:h0} + (({l1:l0} | ({h1:h0} & 1)) > 2^63): round to nearest, ties to even
+inline void round_rne64(uint32_t& m0, uint32_t& m1, uint32_t h0, uint32_t h1, uint32_t l0, uint32_t l1)
+{
+    const uint64_t h = ((uint64_t)h1 << 32) | h0, l = (((uint64_t)l1 << 32) | l0) | (h & 1u);
+    const uint64_t m = h + (l > 0x8000000000000000ull ? 1u : 0u);
+    m0 = (uint32_t)m; m1 = (uint32_t)(m >> 32);
+}
+// x = a + (b ^ mask) + (mask & 1) over 128 bits (a0 == 0)
+inline void addsub128(uint32_t (&x)[4], uint32_t a1, uint32_t a2, uint32_t a3, const uint32_t (&b)[4], uint32_t mask)
+{
+    uint64_t c = mask & 1u, t;
+    t = (uint64_t)0  + (b[0] ^ mask) + c; x[0] = (uint32_t)t; c = t >> 32;
+    t = (uint64_t)a1 + (b[1] ^ mask) + c; x[1] = (uint32_t)t; c = t >> 32;
+    t = (uint64_t)a2 + (b[2] ^ mask) + c; x[2] = (uint32_t)t; c = t >> 32;
+    t = (uint64_t)a3 + (b[3] ^ mask) + c; x[3] = (uint32_t)t;
+}
+#else
+// PTX shifts clamp the count at the register width, so a count of 64 gives 0
+MDZ_HD uint64_t shr64c(uint64_t x, uint32_t n) { uint64_t r; asm("shr.b64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n)); return r; }
+MDZ_HD uint64_t shl64c(uint64_t x, uint32_t n) { uint64_t r; asm("shl.b64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n)); return r; }
+// round up iff (l | (h & 1)) > 2^63  <=>  (l | (h & 1)) + (2^63 - 1) carries out of 64 bits
+MDZ_HD void round_rne64(uint32_t& m0, uint32_t& m1, uint32_t h0, uint32_t h1, uint32_t l0, uint32_t l1)
+{
+    const uint32_t w0 = l0 | (h0 & 1u);
+    uint32_t junk;
+    asm("{\n\t"
+        "add.cc.u32  %2, %3, 0xffffffff;\n\t"
+        "addc.cc.u32 %2, %4, 0x7fffffff;\n\t"
+        "addc.cc.u32 %0, %5, 0;\n\t"
+        "addc.u32    %1, %6, 0;\n\t"
+        "}" : "=&r"(m0), "=&r"(m1), "=&r"(junk) : "r"(w0), "r"(l1), "r"(h0), "r"(h1));
+}
+MDZ_HD void addsub128(uint32_t (&x)[4], uint32_t a1, uint32_t a2, uint32_t a3, const uint32_t (&b)[4], uint32_t mask)
+{
+    uint32_t junk;
+    asm("{\n\t"
+        "add.cc.u32  %4, %5, 0xffffffff;\n\t"       // carry in = 1 when subtracting
+        "addc.cc.u32 %0, %6, 0;\n\t"
+        "addc.cc.u32 %1, %7, %10;\n\t"
+        "addc.cc.u32 %2, %8, %11;\n\t"
+        "addc.u32    %3, %9, %12;\n\t"
+        "}" : "=&r"(x[0]), "=&r"(x[1]), "=&r"(x[2]), "=&r"(x[3]), "=&r"(junk)
+            : "r"(mask & 1u), "r"(b[0] ^ mask), "r"(b[1] ^ mask), "r"(b[2] ^ mask), "r"(b[3] ^ mask),
+              "r"(a1), "r"(a2), "r"(a3));
+}
+#endif
+
+// r = RN(a * b): the sign is left to the caller.  A product just below a power of two
+// (top bit at 126, all ones after the one-bit shift) can round up past 2^64; the top-bit
+// test catches that and a zero operand.
+MDZ_HD void mul64_spec(const Num<2>& a, const Num<2>& b, Num<2>& r, bool& rare)
+{
+    const uint64_t p00 = (uint64_t)a.m[0] * b.m[0];
+    const uint64_t t   = (uint64_t)a.m[1] * b.m[0] + (uint32_t)(p00 >> 32);
+    const uint64_t u   = (uint64_t)a.m[0] * b.m[1] + (uint32_t)t;
+    const uint64_t hi  = (uint64_t)a.m[1] * b.m[1] + (uint32_t)(t >> 32) + (uint32_t)(u >> 32);
+    const uint32_t p0 = (uint32_t)p00, p1 = (uint32_t)u, p2 = (uint32_t)hi, p3 = (uint32_t)(hi >> 32);
+    const uint32_t sh = (p3 >> 31) ^ 1u;             // top bit at 127 or 126
+    const uint32_t x3 = fsl(p2, p3, sh), x2 = fsl(p1, p2, sh), x1 = fsl(p0, p1, sh), x0 = p0 << sh;
+    round_rne64(r.m[0], r.m[1], x2, x3, x0, x1);
+    r.e = a.e + b.e - (int32_t)sh;
+    rare = rare || (int32_t)r.m[1] >= 0 || r.e < E_MIN;
+}
+
+// r = RN(a + b) with the signs as given
+MDZ_HD void add64_spec(const Num<2>& a, const Num<2>& b, Num<2>& r, bool& rare)
+{
+    const int32_t d = a.e - b.e;
+    const uint64_t am = ((uint64_t)a.m[1] << 32) | a.m[0], bm = ((uint64_t)b.m[1] << 32) | b.m[0];
+    const bool swap = d < 0 || (d == 0 && am < bm);             // |A| >= |B| afterwards
+    const uint32_t A0 = swap ? b.m[0] : a.m[0], A1 = swap ? b.m[1] : a.m[1];
+    const uint64_t Bm = swap ? am : bm;
+    const int32_t Ae = swap ? b.e : a.e;
+    const uint32_t ad = (uint32_t)(d < 0 ? -d : d);
+    rare = rare || ad > 62u;
+    // 128-bit frame with one bit of headroom: A >> 1, B >> (ad + 1); nothing of B
+    // leaves the frame while ad <= 62, so the sum is exact
+    const uint64_t BH = shr64c(Bm, ad + 1u), BL = shl64c(Bm, 63u - ad);
+    const uint32_t bw[4] = { (uint32_t)BL, (uint32_t)(BL >> 32), (uint32_t)BH, (uint32_t)(BH >> 32) };
+    const uint32_t mask = (a.s != b.s) ? 0xffffffffu : 0u;
+    uint32_t x[4];
+    addsub128(x, A0 << 31, fsr(A0, A1, 1), A1 >> 1, bw, mask);
+    // normalise: whole word first (32..63 cancelled bits), then bits
+    int32_t e = Ae + 1;
+    if (x[3] == 0) { x[3] = x[2]; x[2] = x[1]; x[1] = x[0]; x[0] = 0; e -= 32; }
+    const uint32_t lz = (uint32_t)clz32(x[3]);       // 32 when still zero: flagged below
+    const uint32_t h1 = fsl(x[2], x[3], lz), h0 = fsl(x[1], x[2], lz), l1 = fsl(x[0], x[1], lz), l0 = x[0] << lz;
+    round_rne64(r.m[0], r.m[1], h0, h1, l0, l1);
+    // top bit clear: >= 64 bits cancelled / exact zero, or the increment carried out
+    rare = rare || (int32_t)r.m[1] >= 0;
+    r.e = e - (int32_t)lz;
+    r.s = swap ? b.s : a.s;
+}
+
+template <>
+MDZ_HD bool pixel_step_spec<2>(PixelState<2>& st, const uint32_t* cre_m, const uint32_t* cim_m,
+                               uint32_t* scr, const RoundCfg& rc, bool abs_im, int abs_re, uint32_t& rare_out)
+{
+    ++st.iter;
+    bool rare = rc.ulp != 1u;                        // precision below 64 bits: general code only
+    Num<2> cim, cre, t, u, nw;
+    cim.m[0] = cim_m[0]; cim.m[1] = cim_m[kScratchStride]; cim.e = st.cim_e; cim.s = st.cim_s;
+    cre.m[0] = cre_m[0]; cre.m[1] = cre_m[kScratchStride]; cre.e = st.cre_e; cre.s = st.cre_s;
+    // wim = 2*wre*wim + c_im
+    mul64_spec(st.wre, st.wim, t, rare);
+    t.e += 1;
+    t.s = abs_im ? 0u : (st.wre.s ^ st.wim.s);
+    // wre = wre2 - wim2 + c_re
+    nw = st.wim2; nw.s = 1u;
+    add64_spec(st.wre2, nw, u, rare);
+    if (abs_re == 1 || (abs_re == 2 && (st.iter & 1))) u.s = 0;
+    add64_spec(t, cim, st.wim, rare);
+    add64_spec(u, cre, st.wre, rare);
+    mul64_spec(st.wim, st.wim, st.wim2, rare);
+    mul64_spec(st.wre, st.wre, st.wre2, rare);
+    st.wim2.s = 0; st.wre2.s = 0;
+    rare_out |= rare ? 1u : 0u;
+    const int32_t emax = st.wim2.e > st.wre2.e ? st.wim2.e : st.wre2.e;
+    bool esc = emax >= 4;
+    if (!rare && !esc && emax >= 2) {
+        // RN(wim2 + wre2) > 4 can only be in doubt when the larger square is in [2, 8)
+        MDZ_COUNT(CNT_ESC_ADD);
+        Num<2> sum; bool r2 = false;
+        add64_spec(st.wim2, st.wre2, sum, r2);
+        if (r2) fadd<2, MODE_ADD_POS>(st.wim2, st.wre2, sum, rc, scr);
+        esc = greater_than_4<2>(sum);
+    }
+    return esc;
+}
+
+}  // namespace mdz

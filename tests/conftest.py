@@ -20,7 +20,7 @@ def emu_lib():
     src = os.path.join(ROOT, "tests", "host_emu", "emu.cpp")
     out = os.path.join(ROOT, "tests", "host_emu", "libmdzemu.so")
     deps = [src] + [os.path.join(ROOT, "mdz_b200", "csrc", f)
-                    for f in ("limb_ops.cuh", "mpfr_sf.cuh", "escape_step.cuh", "mp_convert.h", "mpf_sf.cuh")]
+                    for f in ("limb_ops.cuh", "mpfr_sf.cuh", "escape_step.cuh", "ld64_step.cuh", "mp_convert.h", "mpf_sf.cuh", "mpf_fast.cuh")]
     deps = [d for d in deps if os.path.exists(d)]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out, src])

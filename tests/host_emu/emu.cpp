@@ -7,6 +7,7 @@
 // and has no CPU fallback.
 #define MDZ_HOST_EMU 1
 #include "../../mdz_b200/csrc/escape_step.cuh"
+#include "../../mdz_b200/csrc/ld64_step.cuh"
 #include "../../mdz_b200/csrc/mp_convert.h"
 
 using namespace mdz;
@@ -53,6 +54,22 @@ extern "C" int emu_binop(int op, long prec,
     }
 }
 
+
+// ---- p = 64 fast operations (ld64_step.cuh): result + "rare" flag --------------------
+// op 0: mul (sign = product of signs), 2: add, 3: sub.  Returns 1 when the operation
+// declared itself outside its covered domain (the kernel then uses the general code).
+extern "C" int emu_ld64_op(int op, uint64_t am, int as, long ae, uint64_t bm, int bs, long be,
+                           uint64_t* rm, int* rs, long* re)
+{
+    Num<2> a, b, r;
+    if (as == 0) set_zero(a); else { a.m[0] = (uint32_t)am; a.m[1] = (uint32_t)(am >> 32); a.e = (int32_t)ae; a.s = as < 0; }
+    if (bs == 0) set_zero(b); else { b.m[0] = (uint32_t)bm; b.m[1] = (uint32_t)(bm >> 32); b.e = (int32_t)be; b.s = bs < 0; }
+    bool rare = false;
+    if (op == 0) { mul64_spec(a, b, r, rare); r.s = a.s ^ b.s; }
+    else { if (op == 3) b.s ^= 1u; add64_spec(a, b, r, rare); }
+    *rm = ((uint64_t)r.m[1] << 32) | r.m[0]; *rs = r.s ? -1 : 1; *re = r.e;
+    return rare ? 1 : 0;
+}
 
 // ---- whole-pixel emulation: the kernel's pixel_init / pixel_step on the host ----
 template <int N>

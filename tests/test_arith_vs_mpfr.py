@@ -180,3 +180,46 @@ def test_products_next_to_rounding_boundaries(emu, prec):
             assert emu_op(emu, 1, prec, A, A) == mpfr_op("sqr", prec, A, A), hex(a)
             four += 1
     assert four > 100
+
+
+# ---- the p = 64 fast operations of ld64_step.cuh (long double mode) -----------------------
+def test_ld64_fast_ops_match_libmpfr_or_decline(emu):
+    """mul64_spec / add64_spec either give exactly libmpfr's result at precision 64 or
+    raise their `rare` flag (the kernel then redoes the iteration with the general code);
+    and they do not decline inside the domain they claim: gaps <= 62, fewer than 64
+    cancelled bits, non-zero operands, no carry out of the rounding increment."""
+    emu.emu_ld64_op.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_long, C.c_uint64, C.c_int, C.c_long,
+                                U64P, C.POINTER(C.c_int), C.POINTER(C.c_long)]
+    rng = random.Random(640064)
+    prec = 64
+    declined = {0: 0, 2: 0, 3: 0}
+    for k in range(40000):
+        a, b = rand_pair(rng, prec)
+        if k % 7 == 0:          # near-cancellation with the exponents one apart
+            sa, ea, ma = a.parts()
+            if sa:
+                b = Mpfr(prec).set_parts(sa, ea + rng.choice([-1, 0, 1]), (ma ^ rng.getrandbits(rng.randrange(1, 64))) | (1 << 63))
+        if k % 11 == 0:         # product within a few units of a power of two: the increment can carry out
+            sa, ea, ma = a.parts()
+            if sa:
+                q = (1 << 127) // ma + rng.randrange(-2, 3)
+                q = min(max(q, 1 << 63), (1 << 64) - 1)
+                b = Mpfr(prec).set_parts(rng.choice([1, -1]), rng.randrange(-3, 3), q)
+        sa, ea, ma = a.parts()
+        sb, eb, mb = b.parts()
+        for op, name in ((0, "mul"), (2, "add"), (3, "sub")):
+            rm, rs, re_ = C.c_uint64(), C.c_int(), C.c_long()
+            rare = emu.emu_ld64_op(op, ma, sa, ea, mb, sb, eb, C.byref(rm), C.byref(rs), C.byref(re_))
+            want = mpfr_op(name, prec, a, b)
+            if rare:
+                declined[op] += 1
+                covered = sa != 0 and sb != 0 and (op == 0 or abs(ea - eb) <= 62) and want[0] != 0
+                if covered and op == 0:
+                    covered = want[2] != 1 << 63
+                if covered and op != 0:
+                    # the only excuses left: >= 64 bits cancelled, or the rounding carried out
+                    covered = want[1] > max(ea, eb) - 63 and want[2] != 1 << 63
+                assert not covered, (name, a.parts(), b.parts(), want)
+            else:
+                assert (rs.value, re_.value, rm.value) == want, (name, a.parts(), b.parts(), want)
+    assert declined[0] < 2500 and declined[2] < 12000 and declined[3] < 12000, declined
