@@ -70,7 +70,7 @@ template <int N> struct SmemWords {
 
 // resident blocks per SM the register allocator is asked to make room for
 template <int N> struct MinBlocks {
-    static constexpr int value = N <= 3 ? 8 : N <= 5 ? 6 : N <= 8 ? 5 : N <= 12 ? 4 : N <= 16 ? 3 : N <= 24 ? 2 : 1;
+    static constexpr int value = N <= 2 ? 6 : N <= 3 ? 8 : N <= 5 ? 6 : N <= 8 ? 5 : N <= 12 ? 4 : N <= 16 ? 3 : N <= 24 ? 2 : 1;
 };
 
 template <int N>
@@ -144,6 +144,38 @@ escape_mpfr_kernel(const EscapeParams p)
 
         // ---- iterate ------------------------------------------------------
         uint32_t rare_seen = 0;
+        bool event_loop = false;
+        if constexpr (N == 2) event_loop = use_spec;
+        if (event_loop) {
+            // Long double mode (ld64_step.cuh).  The iteration is one branch-free block that
+            // every lane runs, finished lanes included (their results are ignored); the warp
+            // leaves that block only when some lane has an event -- escaped, reached depth,
+            // or met a case the fast step declines -- so an interior pixel's ten thousand
+            // iterations cost one vote and one branch each on top of the arithmetic.
+            if constexpr (N == 2) {
+                for (int k = 0; k < p.chunk; ++k) {
+                    PixelState<2> nx = st;
+                    uint32_t rare = 0;
+                    bool esc = pixel_step_spec<2>(nx, cre_m, cim_m, scr, p.rc, abs_im, abs_re, rare);
+                    const bool ev = active && (rare != 0 || esc || nx.iter >= p.depth);
+                    if (!__any_sync(0xffffffffu, ev)) { st = nx; continue; }
+                    if (active) {
+                        if (rare != 0) { rare_seen += 1; esc = pixel_step<2>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re); }
+                        else st = nx;
+                        if (esc || st.iter >= p.depth) {
+                            p.raw[pix] = esc ? st.iter : 0;
+                            __threadfence();
+                            active = false;
+                            const unsigned band = (pix / (unsigned)p.width) / (unsigned)p.aa;
+                            const unsigned done = atomicAdd(&p.band_count[band], 1u) + 1u;
+                            if (done == (unsigned)p.width * (unsigned)p.aa) finished_band = (int)band;
+                        }
+                    }
+                    if (publish_bands(p, finished_band, lane)) finished_band = -1;
+                    if (!__any_sync(0xffffffffu, active)) break;
+                }
+            }
+        } else
         for (int k = 0; k < p.chunk; ++k) {
             if (active) {
                 bool esc;

@@ -12,7 +12,7 @@
 // carry chain.  The whole iteration is one basic block.  Everything outside the
 // covered domain raises `rare`, and the caller (pixel_step_auto) redoes the iteration
 // with the general step, so results are those of the general code by construction:
-//   covered:  exponent gap of an addition <= 62, fewer than 64 cancelled bits,
+//   covered:  exponent gap of an addition <= 62, fewer than 31 cancelled bits,
 //             no zero / underflowed operand, no rounding carry out of the top bit.
 #pragma once
 #include "escape_step.cuh"
@@ -104,13 +104,14 @@ MDZ_HD void add64_spec(const Num<2>& a, const Num<2>& b, Num<2>& r, bool& rare)
     const uint32_t mask = (a.s != b.s) ? 0xffffffffu : 0u;
     uint32_t x[4];
     addsub128(x, A0 << 31, fsr(A0, A1, 1), A1 >> 1, bw, mask);
-    // normalise: whole word first (32..63 cancelled bits), then bits
-    int32_t e = Ae + 1;
-    if (x[3] == 0) { x[3] = x[2]; x[2] = x[1]; x[1] = x[0]; x[0] = 0; e -= 32; }
-    const uint32_t lz = (uint32_t)clz32(x[3]);       // 32 when still zero: flagged below
+    // normalise.  31 or more cancelled bits (top word zero, about one addition in a million
+    // on orbit data) are left to the general code: lz is then 32, the funnel shifts move
+    // nothing, and the zero top word fails the top-bit test below
+    const int32_t e = Ae + 1;
+    const uint32_t lz = (uint32_t)clz32(x[3]);
     const uint32_t h1 = fsl(x[2], x[3], lz), h0 = fsl(x[1], x[2], lz), l1 = fsl(x[0], x[1], lz), l0 = x[0] << lz;
     round_rne64(r.m[0], r.m[1], h0, h1, l0, l1);
-    // top bit clear: >= 64 bits cancelled / exact zero, or the increment carried out
+    // top bit clear: >= 31 bits cancelled / exact zero, or the increment carried out
     rare = rare || (int32_t)r.m[1] >= 0;
     r.e = e - (int32_t)lz;
     r.s = swap ? b.s : a.s;
