@@ -92,6 +92,18 @@ mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* view, int device,
  * for A/B measurements), resident blocks per SM (0 = occupancy maximum). */
 int mdzcuda_plan_tune(mdzcuda_plan*, int chunk_iters, int blocks_per_sm);
 
+/*
+ * Exact periodicity check (off by default for a plan; MDZCUDA_CYCLE_DETECT=1 turns it on
+ * for every plan, and the rth_* layer turns it on unless MDZCUDA_CYCLE_DETECT=0).  When the
+ * orbit's state (wre, wim) repeats bit for bit, the reference's loop
+ * (`for (wz = 1; wz <= depth; ++wz)`, src/frac_mandel.c:11-19 / :34-50) can only run to
+ * depth and return 0, so the pixel is finished with 0 at once: identical raw_data, a
+ * fraction of the iterations for views with interior pixels.  Long double and MPFR modes;
+ * ignored in GMP mode.  Throughput figures (bench.py `value`, `e2e`) are measured with it
+ * off, because with it on "iterations performed" is no longer the reference's count.
+ */
+int mdzcuda_plan_set_cycle_detection(mdzcuda_plan*, int on);
+
 /* Enqueue the reset + escape-time kernel on `cuda_stream` (a cudaStream_t; NULL
  * = the legacy default stream).  Asynchronous. */
 int mdzcuda_plan_launch(mdzcuda_plan*, void* cuda_stream);

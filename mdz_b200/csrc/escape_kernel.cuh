@@ -73,7 +73,60 @@ template <int N> struct MinBlocks {
     static constexpr int value = N <= 2 ? 6 : N <= 3 ? 8 : N <= 5 ? 6 : N <= 8 ? 5 : N <= 12 ? 4 : N <= 16 ? 3 : N <= 24 ? 2 : 1;
 };
 
+// ---------------------------------------------------------------------------
+// Exact periodicity check (optional, EscapeParams::cycle).  The recurrence is
+// deterministic, so if (wre, wim) at iteration j equals, bit for bit, the state saved
+// at an earlier iteration i (same parity of j - i for the hybrid fractal, whose step
+// depends on the iteration number's parity, src/frac_variant.c:42-43), the orbit repeats
+// the iterations i..j for ever; none of them escaped, so none ever will, and the
+// reference's loop would run to `depth` and return 0.  The pixel is finished with 0
+// right there: identical raw_data, without the remaining iterations.  Brent's schedule:
+// the state is saved at iterations 1, 2, 4, 8, ...  The saved state lives in a
+// per-thread column of global memory (touched ~log2(depth) times per pixel); two
+// filter words stay in registers, so an iteration pays two compares.
+// ---------------------------------------------------------------------------
+struct CycleState {
+    uint32_t f0, f1;        // wre.m[0], wim.m[0] of the saved state
+    int next;               // iteration at which to save again
+};
+
 template <int N>
+__device__ __forceinline__ void cycle_save(const EscapeParams& p, const PixelState<N>& st, CycleState& cs)
+{
+    uint32_t* col = p.cycle_scratch + (size_t)blockIdx.x * kBlock + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * kBlock;
+#pragma unroll
+    for (int k = 0; k < N; ++k) { col[(size_t)k * stride] = st.wre.m[k]; col[(size_t)(N + k) * stride] = st.wim.m[k]; }
+    col[(size_t)(2 * N) * stride] = (uint32_t)st.wre.e;
+    col[(size_t)(2 * N + 1) * stride] = (uint32_t)st.wim.e;
+    col[(size_t)(2 * N + 2) * stride] = st.wre.s | (st.wim.s << 1) | ((uint32_t)(st.iter & 1) << 2);
+    cs.f0 = st.wre.m[0]; cs.f1 = st.wim.m[0];
+    cs.next = st.iter < (1 << 30) ? (st.iter > 0 ? st.iter * 2 : 1) : 0x7fffffff;
+}
+
+// full comparison after the filter words matched
+template <int N>
+__device__ __noinline__ bool cycle_match(const EscapeParams& p, const PixelState<N>& st)
+{
+    const uint32_t* col = p.cycle_scratch + (size_t)blockIdx.x * kBlock + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * kBlock;
+    uint32_t diff = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        diff |= col[(size_t)k * stride] ^ st.wre.m[k];
+        diff |= col[(size_t)(N + k) * stride] ^ st.wim.m[k];
+    }
+    diff |= col[(size_t)(2 * N) * stride] ^ (uint32_t)st.wre.e;
+    diff |= col[(size_t)(2 * N + 1) * stride] ^ (uint32_t)st.wim.e;
+    uint32_t tag = st.wre.s | (st.wim.s << 1) | ((uint32_t)(st.iter & 1) << 2);
+    uint32_t dt = col[(size_t)(2 * N + 2) * stride] ^ tag;
+    if (p.fractal != FRACTAL_VARIANT) dt &= 3u;        // parity only matters for the hybrid
+    return (diff | dt) == 0;
+}
+
+// CYC: compiled with the exact periodicity check.  A separate instantiation, because the
+// extra state and cold paths cost the plain kernels 7-15 % when merely present.
+template <int N, bool CYC>
 __global__ void __launch_bounds__(kBlock, MinBlocks<N>::value)
 escape_mpfr_kernel(const EscapeParams p)
 {
@@ -98,6 +151,7 @@ escape_mpfr_kernel(const EscapeParams p)
     bool active = false;
     int finished_band = -1;
     bool exhausted = false;         // warp-uniform
+    CycleState cyc; cyc.f0 = 0; cyc.f1 = 0; cyc.next = 0x7fffffff;
     bool use_spec = SpecLimbs<N>::value && p.spec != 0;     // warp-uniform
     int spec_pause = 0, spec_backoff = 8;
     unsigned pix = 0;
@@ -136,6 +190,7 @@ escape_mpfr_kernel(const EscapeParams p)
                         } else { cx = x; cy = y; }
                         pixel_init<N>(st, x, y, cx, cy, p.rc, cre_m, cim_m);
                         active = true;
+                        if (CYC) cycle_save<N>(p, st, cyc);
                     }
                 }
             }
@@ -157,12 +212,18 @@ escape_mpfr_kernel(const EscapeParams p)
                     PixelState<2> nx = st;
                     uint32_t rare = 0;
                     bool esc = pixel_step_spec<2>(nx, cre_m, cim_m, scr, p.rc, abs_im, abs_re, rare);
-                    const bool ev = active && (rare != 0 || esc || nx.iter >= p.depth);
+                    const bool cyc_ev = CYC && ((nx.wre.m[0] == cyc.f0 && nx.wim.m[0] == cyc.f1) || nx.iter == cyc.next);
+                    const bool ev = active && (rare != 0 || esc || nx.iter >= p.depth || cyc_ev);
                     if (!__any_sync(0xffffffffu, ev)) { st = nx; continue; }
                     if (active) {
                         if (rare != 0) { rare_seen += 1; esc = pixel_step<2>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re); }
                         else st = nx;
-                        if (esc || st.iter >= p.depth) {
+                        bool periodic = false;
+                        if (CYC && !esc) {
+                            if (st.wre.m[0] == cyc.f0 && st.wim.m[0] == cyc.f1) periodic = cycle_match<2>(p, st);
+                            if (!periodic && st.iter >= cyc.next) cycle_save<2>(p, st, cyc);
+                        }
+                        if (esc || periodic || st.iter >= p.depth) {
                             p.raw[pix] = esc ? st.iter : 0;
                             __threadfence();
                             active = false;
@@ -184,7 +245,12 @@ escape_mpfr_kernel(const EscapeParams p)
                 else
                     esc = pixel_step<N>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re);
                 const int iter = st.iter;
-                if (esc || iter >= p.depth) {
+                bool periodic = false;
+                if (CYC && !esc) {
+                    if (st.wre.m[0] == cyc.f0 && st.wim.m[0] == cyc.f1) periodic = cycle_match<N>(p, st);
+                    if (!periodic && iter >= cyc.next) cycle_save<N>(p, st, cyc);
+                }
+                if (esc || periodic || iter >= p.depth) {
                     p.raw[pix] = esc ? iter : 0;
                     __threadfence();            // raw visible before the band counter moves
                     active = false;

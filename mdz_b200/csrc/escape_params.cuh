@@ -37,6 +37,8 @@ struct EscapeParams {
     int fractal;
     int chunk;              // iterations between refills
     int spec;               // 1: try the speculative branch-free iteration first
+    int cycle;              // 1: exact periodicity check (escape_kernel.cuh); MPFR / long double kernels only
+    uint32_t* cycle_scratch;    // [2N+3][grid threads] saved states, when cycle != 0
     ColourParams colour;    // fused epilogue: colour a band as soon as it completes (enabled = 0: raw only)
 };
 

@@ -2,23 +2,23 @@
 #include "escape_params.cuh"
 using namespace mdz;
 typedef void (*kernel_fn)(const EscapeParams);
-kernel_fn kernels_mpfr_a_kernel(int n); int kernels_mpfr_a_smem(int n);
-kernel_fn kernels_mpfr_b_kernel(int n); int kernels_mpfr_b_smem(int n);
-kernel_fn kernels_mpfr_c_kernel(int n); int kernels_mpfr_c_smem(int n);
-kernel_fn kernels_mpfr_d_kernel(int n); int kernels_mpfr_d_smem(int n);
-kernel_fn kernels_mpfr_e_kernel(int n); int kernels_mpfr_e_smem(int n);
-kernel_fn kernels_mpfr_f_kernel(int n); int kernels_mpfr_f_smem(int n);
-kernel_fn kernels_mpfr_g_kernel(int n); int kernels_mpfr_g_smem(int n);
-kernel_fn mdz_kernel_mpfr(int n)
+kernel_fn kernels_mpfr_a_kernel(int n, int cyc); int kernels_mpfr_a_smem(int n);
+kernel_fn kernels_mpfr_b_kernel(int n, int cyc); int kernels_mpfr_b_smem(int n);
+kernel_fn kernels_mpfr_c_kernel(int n, int cyc); int kernels_mpfr_c_smem(int n);
+kernel_fn kernels_mpfr_d_kernel(int n, int cyc); int kernels_mpfr_d_smem(int n);
+kernel_fn kernels_mpfr_e_kernel(int n, int cyc); int kernels_mpfr_e_smem(int n);
+kernel_fn kernels_mpfr_f_kernel(int n, int cyc); int kernels_mpfr_f_smem(int n);
+kernel_fn kernels_mpfr_g_kernel(int n, int cyc); int kernels_mpfr_g_smem(int n);
+kernel_fn mdz_kernel_mpfr(int n, int cyc)
 {
     kernel_fn f = nullptr;
-    if (!f) f = kernels_mpfr_a_kernel(n);
-    if (!f) f = kernels_mpfr_b_kernel(n);
-    if (!f) f = kernels_mpfr_c_kernel(n);
-    if (!f) f = kernels_mpfr_d_kernel(n);
-    if (!f) f = kernels_mpfr_e_kernel(n);
-    if (!f) f = kernels_mpfr_f_kernel(n);
-    if (!f) f = kernels_mpfr_g_kernel(n);
+    if (!f) f = kernels_mpfr_a_kernel(n, cyc);
+    if (!f) f = kernels_mpfr_b_kernel(n, cyc);
+    if (!f) f = kernels_mpfr_c_kernel(n, cyc);
+    if (!f) f = kernels_mpfr_d_kernel(n, cyc);
+    if (!f) f = kernels_mpfr_e_kernel(n, cyc);
+    if (!f) f = kernels_mpfr_f_kernel(n, cyc);
+    if (!f) f = kernels_mpfr_g_kernel(n, cyc);
     return f;
 }
 int mdz_smem_words_mpfr(int n)

@@ -3,16 +3,16 @@
 #include "escape_kernel.cuh"
 using namespace mdz;
 typedef void (*kernel_fn)(const EscapeParams);
-kernel_fn kernels_mpfr_a_kernel(int n)
+kernel_fn kernels_mpfr_a_kernel(int n, int cyc)
 {
     switch (n) {
-    case 2: return escape_mpfr_kernel<2>;
-    case 3: return escape_mpfr_kernel<3>;
-    case 4: return escape_mpfr_kernel<4>;
-    case 5: return escape_mpfr_kernel<5>;
-    case 6: return escape_mpfr_kernel<6>;
-    case 7: return escape_mpfr_kernel<7>;
-    case 8: return escape_mpfr_kernel<8>;
+    case 2: return cyc ? escape_mpfr_kernel<2, true> : escape_mpfr_kernel<2, false>;
+    case 3: return cyc ? escape_mpfr_kernel<3, true> : escape_mpfr_kernel<3, false>;
+    case 4: return cyc ? escape_mpfr_kernel<4, true> : escape_mpfr_kernel<4, false>;
+    case 5: return cyc ? escape_mpfr_kernel<5, true> : escape_mpfr_kernel<5, false>;
+    case 6: return cyc ? escape_mpfr_kernel<6, true> : escape_mpfr_kernel<6, false>;
+    case 7: return cyc ? escape_mpfr_kernel<7, true> : escape_mpfr_kernel<7, false>;
+    case 8: return cyc ? escape_mpfr_kernel<8, true> : escape_mpfr_kernel<8, false>;
     default: return nullptr;
     }
 }

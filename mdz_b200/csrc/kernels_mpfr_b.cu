@@ -3,13 +3,13 @@
 #include "escape_kernel.cuh"
 using namespace mdz;
 typedef void (*kernel_fn)(const EscapeParams);
-kernel_fn kernels_mpfr_b_kernel(int n)
+kernel_fn kernels_mpfr_b_kernel(int n, int cyc)
 {
     switch (n) {
-    case 9: return escape_mpfr_kernel<9>;
-    case 10: return escape_mpfr_kernel<10>;
-    case 11: return escape_mpfr_kernel<11>;
-    case 12: return escape_mpfr_kernel<12>;
+    case 9: return cyc ? escape_mpfr_kernel<9, true> : escape_mpfr_kernel<9, false>;
+    case 10: return cyc ? escape_mpfr_kernel<10, true> : escape_mpfr_kernel<10, false>;
+    case 11: return cyc ? escape_mpfr_kernel<11, true> : escape_mpfr_kernel<11, false>;
+    case 12: return cyc ? escape_mpfr_kernel<12, true> : escape_mpfr_kernel<12, false>;
     default: return nullptr;
     }
 }

@@ -3,13 +3,13 @@
 #include "escape_kernel.cuh"
 using namespace mdz;
 typedef void (*kernel_fn)(const EscapeParams);
-kernel_fn kernels_mpfr_c_kernel(int n)
+kernel_fn kernels_mpfr_c_kernel(int n, int cyc)
 {
     switch (n) {
-    case 13: return escape_mpfr_kernel<13>;
-    case 14: return escape_mpfr_kernel<14>;
-    case 15: return escape_mpfr_kernel<15>;
-    case 16: return escape_mpfr_kernel<16>;
+    case 13: return cyc ? escape_mpfr_kernel<13, true> : escape_mpfr_kernel<13, false>;
+    case 14: return cyc ? escape_mpfr_kernel<14, true> : escape_mpfr_kernel<14, false>;
+    case 15: return cyc ? escape_mpfr_kernel<15, true> : escape_mpfr_kernel<15, false>;
+    case 16: return cyc ? escape_mpfr_kernel<16, true> : escape_mpfr_kernel<16, false>;
     default: return nullptr;
     }
 }

@@ -3,14 +3,14 @@
 #include "escape_kernel.cuh"
 using namespace mdz;
 typedef void (*kernel_fn)(const EscapeParams);
-kernel_fn kernels_mpfr_d_kernel(int n)
+kernel_fn kernels_mpfr_d_kernel(int n, int cyc)
 {
     switch (n) {
-    case 17: return escape_mpfr_kernel<17>;
-    case 18: return escape_mpfr_kernel<18>;
-    case 19: return escape_mpfr_kernel<19>;
-    case 20: return escape_mpfr_kernel<20>;
-    case 21: return escape_mpfr_kernel<21>;
+    case 17: return cyc ? escape_mpfr_kernel<17, true> : escape_mpfr_kernel<17, false>;
+    case 18: return cyc ? escape_mpfr_kernel<18, true> : escape_mpfr_kernel<18, false>;
+    case 19: return cyc ? escape_mpfr_kernel<19, true> : escape_mpfr_kernel<19, false>;
+    case 20: return cyc ? escape_mpfr_kernel<20, true> : escape_mpfr_kernel<20, false>;
+    case 21: return cyc ? escape_mpfr_kernel<21, true> : escape_mpfr_kernel<21, false>;
     default: return nullptr;
     }
 }

@@ -3,14 +3,14 @@
 #include "escape_kernel.cuh"
 using namespace mdz;
 typedef void (*kernel_fn)(const EscapeParams);
-kernel_fn kernels_mpfr_e_kernel(int n)
+kernel_fn kernels_mpfr_e_kernel(int n, int cyc)
 {
     switch (n) {
-    case 22: return escape_mpfr_kernel<22>;
-    case 23: return escape_mpfr_kernel<23>;
-    case 24: return escape_mpfr_kernel<24>;
-    case 25: return escape_mpfr_kernel<25>;
-    case 26: return escape_mpfr_kernel<26>;
+    case 22: return cyc ? escape_mpfr_kernel<22, true> : escape_mpfr_kernel<22, false>;
+    case 23: return cyc ? escape_mpfr_kernel<23, true> : escape_mpfr_kernel<23, false>;
+    case 24: return cyc ? escape_mpfr_kernel<24, true> : escape_mpfr_kernel<24, false>;
+    case 25: return cyc ? escape_mpfr_kernel<25, true> : escape_mpfr_kernel<25, false>;
+    case 26: return cyc ? escape_mpfr_kernel<26, true> : escape_mpfr_kernel<26, false>;
     default: return nullptr;
     }
 }

@@ -3,12 +3,12 @@
 #include "escape_kernel.cuh"
 using namespace mdz;
 typedef void (*kernel_fn)(const EscapeParams);
-kernel_fn kernels_mpfr_f_kernel(int n)
+kernel_fn kernels_mpfr_f_kernel(int n, int cyc)
 {
     switch (n) {
-    case 27: return escape_mpfr_kernel<27>;
-    case 28: return escape_mpfr_kernel<28>;
-    case 29: return escape_mpfr_kernel<29>;
+    case 27: return cyc ? escape_mpfr_kernel<27, true> : escape_mpfr_kernel<27, false>;
+    case 28: return cyc ? escape_mpfr_kernel<28, true> : escape_mpfr_kernel<28, false>;
+    case 29: return cyc ? escape_mpfr_kernel<29, true> : escape_mpfr_kernel<29, false>;
     default: return nullptr;
     }
 }

@@ -3,12 +3,12 @@
 #include "escape_kernel.cuh"
 using namespace mdz;
 typedef void (*kernel_fn)(const EscapeParams);
-kernel_fn kernels_mpfr_g_kernel(int n)
+kernel_fn kernels_mpfr_g_kernel(int n, int cyc)
 {
     switch (n) {
-    case 30: return escape_mpfr_kernel<30>;
-    case 31: return escape_mpfr_kernel<31>;
-    case 32: return escape_mpfr_kernel<32>;
+    case 30: return cyc ? escape_mpfr_kernel<30, true> : escape_mpfr_kernel<30, false>;
+    case 31: return cyc ? escape_mpfr_kernel<31, true> : escape_mpfr_kernel<31, false>;
+    case 32: return cyc ? escape_mpfr_kernel<32, true> : escape_mpfr_kernel<32, false>;
     default: return nullptr;
     }
 }

@@ -314,6 +314,9 @@ struct mdzcuda_plan {
     cudaStream_t side = nullptr;        // progress / cancel traffic while the kernel runs
     cudaEvent_t done_ev = nullptr;
     int chunk = 0, blocks_per_sm = 0, spec = 1;
+    int cycle = 0;                      // exact periodicity check (mdzcuda_plan_set_cycle_detection)
+    uint32_t* d_cycle = nullptr;        // its saved-state columns, allocated at the first launch that needs them
+    size_t cycle_words = 0;
     bool gmp = false;
     mdzcuda_kernel_info info;
     unsigned int* h_pinned = nullptr;   // 4 words of pinned staging
@@ -326,7 +329,7 @@ typedef void (*kernel_fn)(const EscapeParams);
 
 // The kernels are instantiated in separate translation units (kernels_*.cu) so that the
 // build parallelises: one unrolled kernel per limb count is seconds to minutes of ptxas.
-kernel_fn mdz_kernel_mpfr(int n32);             // N = 2..32 words   (kernels_mpfr_*.cu)
+kernel_fn mdz_kernel_mpfr(int n32, int cyc);    // N = 2..32 words, without / with the periodicity check (kernels_mpfr_*.cu)
 int       mdz_smem_words_mpfr(int n32);
 kernel_fn mdz_kernel_gmp_clear(int nl);         // NL = 3..10 limbs  (kernels_gmp.cu)
 kernel_fn mdz_kernel_gmp_fast(int nl);          // NL = 4..10 limbs  (kernels_gmpf_*.cu)
@@ -346,7 +349,7 @@ static int gmp_smem_words(int nl)
     if (getenv("MDZCUDA_GMP_CLEAR")) return 0;
     return mdz_smem_words_gmp_fast(nl);
 }
-static kernel_fn kernel_for_limbs(int n) { return mdz_kernel_mpfr(n); }
+static kernel_fn kernel_for_limbs(int n, int cyc = 0) { return mdz_kernel_mpfr(n, cyc); }
 static int smem_words_for_limbs(int n) { return mdz_smem_words_mpfr(n); }
 
 // ---- prologue: MPFR mode (reference src/fractal.c:143-188) ------------------
@@ -466,6 +469,40 @@ static int prologue_ld(const mdzcuda_view* v, const std::vector<int>& lines,
     return 1;
 }
 
+// kernel facts per (device, kernel) are cached: cudaGetDeviceProperties and the
+// occupancy query cost milliseconds, which is a visible share of a 60 ms render
+static int kernel_facts(int device, kernel_fn fn, int smem, int n32, mdzcuda_kernel_info* out)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, mdzcuda_kernel_info> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(device, (const void*)fn);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        cudaFuncAttributes fa;
+        CUDA_OK(cudaFuncGetAttributes(&fa, (const void*)fn));
+        int sms = 0;
+        CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        if (smem > 48 * 1024)
+            CUDA_OK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int occ = 0;
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, kBlock, smem));
+        if (occ < 1) { set_err("kernel for %d limbs does not fit on an SM", n32); return 0; }
+        mdzcuda_kernel_info ki;
+        ki.limbs = n32;
+        ki.regs_per_thread = fa.numRegs;
+        ki.local_bytes = (int)fa.localSizeBytes;
+        ki.shared_bytes = smem;
+        ki.block_threads = kBlock;
+        ki.blocks_per_sm = occ;
+        ki.sm_count = sms;
+        ki.grid_blocks = occ * sms;
+        it = cache.insert(std::make_pair(key, ki)).first;
+    }
+    *out = it->second;
+    return 1;
+}
+
 extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
                                              int band_first, int band_stride)
 {
@@ -508,6 +545,7 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
     pl->local_lines = (int)pl->line_map.size();
     pl->nbands = pl->local_lines / v->aa_factor;
     pl->gmp = gmp;
+    { const char* e = getenv("MDZCUDA_CYCLE_DETECT"); pl->cycle = (e && *e && *e != '0') ? 1 : 0; }
     pl->rc = make_round_cfg(n32, v->mode == MDZCUDA_MODE_LD ? 64 : (gmp ? 32 * n32 : (int)v->precision));
 
     HostTable xs, ys, jc;
@@ -545,43 +583,20 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
         CUDA_OKP(pool_event(device, &pl->done_ev));
         CUDA_OKP(pool_pinned(device, &pl->h_pinned));                    // staging words for progress / cancel traffic
 
-        // kernel facts per (device, kernel) are cached: cudaGetDeviceProperties and the
-        // occupancy query cost milliseconds, which is a visible share of a 60 ms render
         const int smem = (gmp ? gmp_smem_words(n32 / 2) : smem_words_for_limbs(n32)) * kBlock * (int)sizeof(uint32_t);   // c_re, c_im, shifter scratch, checkpoint
-        {
-            static std::mutex mu;
-            static std::map<std::pair<int, const void*>, mdzcuda_kernel_info> cache;
-            std::lock_guard<std::mutex> lock(mu);
-            auto key = std::make_pair(device, (const void*)fn);
-            auto it = cache.find(key);
-            if (it == cache.end()) {
-                cudaFuncAttributes fa;
-                CUDA_OKP(cudaFuncGetAttributes(&fa, (const void*)fn));
-                int sms = 0;
-                CUDA_OKP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-                if (smem > 48 * 1024)
-                    CUDA_OKP(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                int occ = 0;
-                CUDA_OKP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, kBlock, smem));
-                if (occ < 1) { set_err("kernel for %d limbs does not fit on an SM", n32); goto fail; }
-                mdzcuda_kernel_info ki;
-                ki.limbs = n32;
-                ki.regs_per_thread = fa.numRegs;
-                ki.local_bytes = (int)fa.localSizeBytes;
-                ki.shared_bytes = smem;
-                ki.block_threads = kBlock;
-                ki.blocks_per_sm = occ;
-                ki.sm_count = sms;
-                ki.grid_blocks = occ * sms;
-                it = cache.insert(std::make_pair(key, ki)).first;
-            }
-            pl->info = it->second;
-        }
+        if (!kernel_facts(device, fn, smem, n32, &pl->info)) goto fail;
     }
     return pl;
 fail:
     mdzcuda_plan_destroy(pl);
     return nullptr;
+}
+
+extern "C" int mdzcuda_plan_set_cycle_detection(mdzcuda_plan* pl, int on)
+{
+    if (!pl) { set_err("null plan"); return 0; }
+    pl->cycle = on ? 1 : 0;
+    return 1;
 }
 
 extern "C" int mdzcuda_plan_tune(mdzcuda_plan* pl, int chunk_iters, int blocks_per_sm)
@@ -627,15 +642,31 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         p.chunk = pl->chunk ? pl->chunk : default_chunk(pl->n32);
         p.spec = pl->spec;
         p.colour = pl->colour;
-        int bps = pl->blocks_per_sm ? pl->blocks_per_sm : pl->info.blocks_per_sm;
-        if (bps > pl->info.blocks_per_sm) bps = pl->info.blocks_per_sm;
+        const int cyc = (pl->cycle && !pl->gmp) ? 1 : 0;
+        kernel_fn fn = pl->gmp ? gmp_kernel_for_limbs(pl->n32 / 2) : kernel_for_limbs(pl->n32, cyc);
+        if (!fn) { set_err("no kernel for %d limbs", pl->n32); return 0; }
+        mdzcuda_kernel_info ki;
+        if (!kernel_facts(pl->device, fn, pl->info.shared_bytes, pl->n32, &ki)) return 0;
+        int bps = pl->blocks_per_sm ? pl->blocks_per_sm : ki.blocks_per_sm;
+        if (bps > ki.blocks_per_sm) bps = ki.blocks_per_sm;
         long long npx = (long long)pl->local_lines * pl->view.real_width;
-        long long grid = (long long)bps * pl->info.sm_count;
+        long long grid = (long long)bps * ki.sm_count;
         long long need = (npx + kBlock - 1) / kBlock;
         if (grid > need) grid = need;
-        pl->info.grid_blocks = (int)grid;
-        kernel_fn fn = pl->gmp ? gmp_kernel_for_limbs(pl->n32 / 2) : kernel_for_limbs(pl->n32);
-        fn<<<(unsigned)grid, kBlock, pl->info.shared_bytes, st>>>(p);
+        ki.grid_blocks = (int)grid;
+        pl->info = ki;
+        p.cycle = cyc;
+        p.cycle_scratch = nullptr;
+        if (cyc) {
+            const size_t words = (size_t)(2 * pl->n32 + 3) * (size_t)grid * kBlock;
+            if (words > pl->cycle_words) {
+                if (pl->d_cycle) { CUDA_OK(cudaStreamSynchronize(st)); pool_free(pl->device, pl->d_cycle); pl->d_cycle = nullptr; }
+                CUDA_OK(pool_alloc(pl->device, (void**)&pl->d_cycle, words * sizeof(uint32_t)));
+                pl->cycle_words = words;
+            }
+            p.cycle_scratch = pl->d_cycle;
+        }
+        fn<<<(unsigned)grid, kBlock, ki.shared_bytes, st>>>(p);
         CUDA_OK(cudaGetLastError());
     }
     CUDA_OK(cudaEventRecord(pl->done_ev, st));
@@ -788,7 +819,7 @@ extern "C" void mdzcuda_plan_destroy(mdzcuda_plan* pl)
     if (pl->side) cudaStreamSynchronize(pl->side);
     DevPool& P = g_pool[pl->device];
     pool_free(pl->device, pl->d_palette); pool_free(pl->device, pl->d_rgb);
-    pool_free(pl->device, pl->d_raw); pool_free(pl->device, pl->d_arena);
+    pool_free(pl->device, pl->d_raw); pool_free(pl->device, pl->d_arena); pool_free(pl->device, pl->d_cycle);
     {
         std::lock_guard<std::mutex> lock(P.mu);
         if (pl->side) P.streams.push_back(pl->side);

@@ -234,6 +234,9 @@ static void* rth_render_main(void* ptr)
     for (size_t i = 0; err.empty() && i < devs.size(); ++i) {
         mdzcuda_plan* p = mdzcuda_plan_create(&v, devs[i], (int)i, (int)devs.size());
         if (!p) { err = mdzcuda_last_error(); break; }
+        // same raw_data, fewer iterations for interior pixels (include/mdzcuda.h); MDZ's own
+        // callers only ever see the result, so it is on unless MDZCUDA_CYCLE_DETECT=0
+        { const char* e = getenv("MDZCUDA_CYCLE_DETECT"); mdzcuda_plan_set_cycle_detection(p, !(e && *e == '0')); }
         plans.push_back(p);
     }
     for (size_t i = 0; err.empty() && i < plans.size(); ++i)

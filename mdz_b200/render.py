@@ -110,6 +110,10 @@ class Plan:
     def tune(self, chunk_iters=0, blocks_per_sm=0):
         self._chk(_l.lib.mdzcuda_plan_tune(self.h, chunk_iters, blocks_per_sm), "plan_tune")
 
+    def set_cycle_detection(self, on=True):
+        """Exact periodicity check: same raw_data, interior pixels finish early."""
+        self._chk(_l.lib.mdzcuda_plan_set_cycle_detection(self.h, 1 if on else 0), "plan_set_cycle_detection")
+
     def launch(self, stream=None):
         self._chk(_l.lib.mdzcuda_plan_launch(self.h, C.c_void_p(stream or 0)), "plan_launch")
 

@@ -158,3 +158,36 @@ def test_plan_run_delivers_what_fetch_returns_and_pool_reuse(ref_lib):
     for p in plans:
         p.close()
     assert np.array_equal(out, want2)
+
+
+CYCLE_VIEWS = [
+    ("ld cfg2", lambda: config2(320, 180, 3000)),
+    ("ld ship", lambda: make_view("-0.5", "-0.3", "3.5", 160, 120, mode="ld", depth=1500, fractal=BURNING_SHIP)),
+    ("ld celtic", lambda: make_view("-0.5", "-0.3", "3.5", 160, 120, mode="ld", depth=1500, fractal=GENERALIZED_CELTIC)),
+    ("ld hybrid (parity of the period matters)", lambda: make_view("-0.5", "-0.3", "3.5", 160, 120, mode="ld", depth=1500, fractal=VARIANT)),
+    ("ld julia", lambda: make_view("0", "0", "3.2", 120, 90, mode="ld", depth=2000, family=FAMILY_JULIA, julia=("-0.12", "0.74"))),
+    ("mpfr80 interior", lambda: make_view("-0.2", "0.1", "1.5", 96, 72, precision=80, depth=2000)),
+    ("mpfr128 hybrid", lambda: make_view("-0.5", "-0.3", "3.5", 96, 72, precision=128, depth=800, fractal=VARIANT)),
+    ("mpfr320 bulb", lambda: make_view("-1.0", "0.0", "0.6", 64, 48, precision=320, depth=1500)),
+    ("mpfr512 cardioid", lambda: make_view("-0.3", "0.2", "0.8", 48, 36, precision=512, depth=1200)),
+    ("mpfr1024", lambda: make_view("-0.3", "0.2", "0.8", 24, 18, precision=1024, depth=600)),
+]
+
+
+@pytest.mark.parametrize("name,mk", CYCLE_VIEWS, ids=[c[0] for c in CYCLE_VIEWS])
+def test_cycle_detection_changes_nothing(ref_lib, name, mk):
+    """The exact periodicity check (mdzcuda_plan_set_cycle_detection) finishes interior
+    pixels early; raw_data must equal the reference's, which iterates to depth."""
+    v = mk()
+    want, _ = ref_render(ref_lib, v)
+    assert (want == 0).sum() > 50, "view has no interior: the test would prove nothing"
+    for spec in (1, 0):
+        p = mdz_b200.Plan(v, 0)
+        p.set_cycle_detection(True)
+        if not spec:
+            p.tune(-16, 0)
+        got = p.run()
+        p.close()
+        bad = np.argwhere(got != want)
+        assert bad.size == 0, "%s spec=%d: %d mismatching pixels, first %s: got %d want %d" % (
+            name, spec, len(bad), bad[0], got[tuple(bad[0])], want[tuple(bad[0])])

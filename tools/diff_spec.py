@@ -11,10 +11,16 @@ from views import config2
 w, h = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1920, 1080)
 v = config2(w, h, 10000)
 out = []
-for chunk in (32, -32):
+for chunk, cyc in ((32, 0), (-32, 0), (32, 1), (-32, 1)):
     p = mdz_b200.Plan(v, 0)
     p.tune(chunk, 0)
-    p.launch(); out.append(p.fetch()); p.close()
+    p.set_cycle_detection(bool(cyc))
+    import time
+    p.launch(); p.wait(); t0 = time.perf_counter(); p.launch(); p.wait(); dt = time.perf_counter() - t0
+    out.append(p.fetch()); p.close()
+    print("chunk %d cycle %d: %.2f ms" % (chunk, cyc, dt * 1e3))
+for k in (2, 3):
+    print("cycle-detect run %d vs full iteration: %d mismatches" % (k, int((out[k] != out[1]).sum())))
 bad = np.argwhere(out[0] != out[1])
 print("mismatches:", len(bad))
 for line, ix in bad[:40]:

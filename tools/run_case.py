@@ -36,10 +36,12 @@ ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--chunk", type=int, default=0)
 ap.add_argument("--bps", type=int, default=0)
+ap.add_argument("--cycle", type=int, default=0, help="1: exact periodicity check on")
 a = ap.parse_args()
 v = case(a.case, a.scale)
 plan = mdz_b200.Plan(v, 0)
 plan.tune(a.chunk, a.bps)
+plan.set_cycle_detection(bool(a.cycle))
 for i in range(a.reps):
     t0 = time.perf_counter()
     plan.launch()
