@@ -42,7 +42,7 @@ __device__ __forceinline__ bool publish_bands(const EscapeParams& p, int finishe
         __syncwarp();
         __threadfence();
         if (lane == 0) {
-            p.band_flag[band] = 1;
+            p.band_flag[band] = p.gen;
             atomicAdd((unsigned int*)p.bands_done, 1u);
         }
     }
@@ -164,7 +164,7 @@ escape_mpfr_kernel(const EscapeParams p)
         // ---- cooperative cancel (reference polls every 64 px, fractal.c:113) --
         {
             int stop = 0;
-            if (lane == 0) stop = *p.cancel;
+            if (lane == 0) stop = *p.cancel == p.gen;
             if (__shfl_sync(0xffffffffu, stop, 0)) break;
         }
         // ---- refill finished lanes from the queue ------------------------
@@ -318,7 +318,7 @@ escape_gmp_kernel(const EscapeParams p)
     for (;;) {
         {
             int stop = 0;
-            if (lane == 0) stop = *p.cancel;
+            if (lane == 0) stop = *p.cancel == p.gen;
             if (__shfl_sync(0xffffffffu, stop, 0)) break;
         }
         if (!exhausted) {
@@ -411,7 +411,7 @@ escape_gmpf_kernel(const EscapeParams p)
     for (;;) {
         {
             int stop = 0;
-            if (lane == 0) stop = *p.cancel;
+            if (lane == 0) stop = *p.cancel == p.gen;
             if (__shfl_sync(0xffffffffu, stop, 0)) break;
         }
         if (!exhausted) {

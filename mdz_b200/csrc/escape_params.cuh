@@ -27,8 +27,9 @@ struct EscapeParams {
     unsigned int* queue;    // next pixel index
     unsigned int* band_count;   // finished supersamples per band of aa lines
     volatile unsigned int* bands_done;   // number of completed bands
-    unsigned char* band_flag;   // 1 when band complete (device copy, host polls a mirror)
-    const volatile int* cancel; // device stop flag, set by the host from a side stream (rth_ui_stop_render)
+    unsigned int* band_flag;    // [band] = launch generation once the band is complete (host polls a mirror)
+    unsigned int gen;           // this launch's generation: flags left by an earlier launch or plan never match
+    const volatile unsigned int* cancel; // == gen: stop (written by the host from a side stream, rth_ui_stop_render)
     int width;              // real width
     int lines;              // local line count (multiple of aa)
     int aa;

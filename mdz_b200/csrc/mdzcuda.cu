@@ -307,10 +307,14 @@ struct mdzcuda_plan {
     RoundCfg rc;
     int32_t* d_raw = nullptr;
     uint32_t* d_arena = nullptr;        // tables + everything below
-    unsigned int* d_ctrl = nullptr;     // [0] queue, [1] bands_done, [2] cancel
+    unsigned int* d_ctrl = nullptr;     // [0] queue, [1] bands_done
     unsigned int* d_band_count = nullptr;
-    unsigned char* d_band_flag = nullptr;
-    size_t reset_words = 0;             // ctrl + band_count + band_flag, contiguous
+    unsigned int* d_band_flag = nullptr;    // [nbands] generation of the launch that completed the band
+    unsigned int gen = 0;                   // generation of the current launch (1, 2, ...; never 0)
+    std::vector<unsigned int> h_flags;      // host mirror for mdzcuda_plan_poll_bands
+    size_t reset_words = 0;             // ctrl + band_count: reset by every launch, in stream order
+    size_t zero_words = 0;              // ctrl .. cancel word: zeroed once at create
+    unsigned int* d_cancel = nullptr;   // holds the generation of the launch that is to stop (never reset)
     cudaStream_t side = nullptr;        // progress / cancel traffic while the kernel runs
     cudaEvent_t done_ev = nullptr;
     int chunk = 0, blocks_per_sm = 0, spec = 1;
@@ -564,22 +568,32 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
             const size_t table_words = arena_put(ar, jc, o[6], o[7], o[8]);
             const size_t o_ctrl = ar.reserve(4);
             const size_t o_count = ar.reserve((size_t)pl->nbands + 1);
-            const size_t o_flag = ar.reserve(((size_t)pl->nbands + 4) / 4 + 1);
+            const size_t o_flag = ar.reserve((size_t)pl->nbands + 1);
+            const size_t o_cancel = ar.reserve(4);
             CUDA_OKP(pool_alloc(device, (void**)&pl->d_arena, ar.words * sizeof(uint32_t)));
             CUDA_OKP(cudaMemcpy(pl->d_arena, ar.host.data(), table_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
-            CUDA_OKP(cudaMemset(pl->d_arena + o_ctrl, 0, (ar.words - o_ctrl) * sizeof(uint32_t)));   // (the launch resets it again, in stream order)
             uint32_t* b = pl->d_arena;
             pl->xs.m = b + o[0]; pl->xs.e = (int32_t*)(b + o[1]); pl->xs.s = b + o[2]; pl->xs.count = xs.count;
             pl->ys.m = b + o[3]; pl->ys.e = (int32_t*)(b + o[4]); pl->ys.s = b + o[5]; pl->ys.count = ys.count;
             pl->jc.m = b + o[6]; pl->jc.e = (int32_t*)(b + o[7]); pl->jc.s = b + o[8]; pl->jc.count = jc.count;
             pl->d_ctrl = b + o_ctrl;
             pl->d_band_count = b + o_count;
-            pl->d_band_flag = (unsigned char*)(b + o_flag);
-            pl->reset_words = ar.words - o_ctrl;
+            pl->d_band_flag = b + o_flag;
+            pl->d_cancel = b + o_cancel;
+            pl->zero_words = ar.words - o_ctrl;     // everything from the control words on, once, at create
+            pl->reset_words = o_flag - o_ctrl;      // per launch: queue counter and band counters only
         }
         size_t npx = (size_t)pl->local_lines * v->real_width;
         CUDA_OKP(pool_alloc(device, (void**)&pl->d_raw, (npx ? npx : 1) * sizeof(int32_t)));
         CUDA_OKP(pool_stream(device, &pl->side));
+        // Control words, band counters and flags start at zero.  On the side stream, and waited
+        // for: the polls run on that stream, which is not ordered against the caller's, and a
+        // recycled arena still holds the previous plan's flags (a cudaMemset on the default
+        // stream could still be queued when the first poll reads them -- seen once per ~300
+        // strided renders as a frame delivered before it was rendered).
+        CUDA_OKP(cudaMemsetAsync(pl->d_ctrl, 0, pl->zero_words * sizeof(uint32_t), pl->side));
+        CUDA_OKP(cudaStreamSynchronize(pl->side));
+        pl->h_flags.assign((size_t)pl->nbands + 1, 0u);
         CUDA_OKP(pool_event(device, &pl->done_ev));
         CUDA_OKP(pool_pinned(device, &pl->h_pinned));                    // staging words for progress / cancel traffic
 
@@ -623,6 +637,13 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
     cudaStream_t st = (cudaStream_t)cuda_stream;
     CUDA_OK(cudaSetDevice(pl->device));
     CUDA_OK(cudaMemsetAsync(pl->d_ctrl, 0, pl->reset_words * sizeof(uint32_t), st));   // queue, counters, flags
+    {
+        // test hook: fill the iteration buffer with a pattern no render produces, so that a band
+        // delivered before it was complete shows up deterministically (tests/test_parity_gpu.py)
+        static const bool poison = [] { const char* e = getenv("MDZCUDA_DEBUG_POISON"); return e && *e && *e != '0'; }();
+        if (poison && pl->local_lines > 0)
+            CUDA_OK(cudaMemsetAsync(pl->d_raw, 0x7f, (size_t)pl->local_lines * pl->view.real_width * sizeof(int32_t), st));
+    }
     if (pl->local_lines > 0) {
         EscapeParams p;
         p.xs = pl->xs.view(); p.ys = pl->ys.view(); p.jc = pl->jc.view();
@@ -630,9 +651,11 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         p.raw = pl->d_raw;
         p.queue = pl->d_ctrl + 0;
         p.bands_done = pl->d_ctrl + 1;
-        p.cancel = (const volatile int*)(pl->d_ctrl + 2);
+        p.cancel = (const volatile unsigned int*)pl->d_cancel;
         p.band_count = pl->d_band_count;
         p.band_flag = pl->d_band_flag;
+        if (++pl->gen == 0) pl->gen = 1;
+        p.gen = pl->gen;
         p.width = pl->view.real_width;
         p.lines = pl->local_lines;
         p.aa = pl->view.aa_factor;
@@ -685,8 +708,10 @@ extern "C" int mdzcuda_plan_cancel(mdzcuda_plan* pl)
 {
     if (!pl) { set_err("null plan"); return 0; }
     CUDA_OK(cudaSetDevice(pl->device));
-    pl->h_pinned[0] = 1;
-    CUDA_OK(cudaMemcpyAsync(pl->d_ctrl + 2, pl->h_pinned, sizeof(unsigned int), cudaMemcpyHostToDevice, pl->side));
+    // the kernel stops when the word equals its own generation; nothing ever resets the word, so
+    // a stop that arrives before the launch's reset has executed cannot be wiped out by it
+    pl->h_pinned[0] = pl->gen;
+    CUDA_OK(cudaMemcpyAsync(pl->d_cancel, pl->h_pinned, sizeof(unsigned int), cudaMemcpyHostToDevice, pl->side));
     CUDA_OK(cudaStreamSynchronize(pl->side));
     return 1;
 }
@@ -694,10 +719,9 @@ extern "C" int mdzcuda_plan_cancel(mdzcuda_plan* pl)
 extern "C" int mdzcuda_plan_bands_done(mdzcuda_plan* pl)
 {
     if (!pl) { set_err("null plan"); return -1; }
-    if (cudaSetDevice(pl->device) != cudaSuccess) return -1;
-    if (cudaMemcpyAsync(pl->h_pinned + 1, pl->d_ctrl + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, pl->side) != cudaSuccess) return -1;
-    if (cudaStreamSynchronize(pl->side) != cudaSuccess) return -1;
-    return (int)pl->h_pinned[1];
+    if (pl->nbands == 0) return 0;
+    std::vector<unsigned char> f((size_t)pl->nbands);
+    return mdzcuda_plan_poll_bands(pl, f.data());
 }
 
 extern "C" int mdzcuda_plan_bands_total(mdzcuda_plan* pl) { return pl ? pl->nbands : -1; }
@@ -726,10 +750,15 @@ extern "C" int mdzcuda_plan_poll_bands(mdzcuda_plan* pl, unsigned char* flags_ho
     if (!pl || !flags_host) { set_err("null argument"); return -1; }
     if (cudaSetDevice(pl->device) != cudaSuccess) return -1;
     if (pl->nbands == 0) return 0;
-    if (cudaMemcpyAsync(flags_host, pl->d_band_flag, pl->nbands, cudaMemcpyDeviceToHost, pl->side) != cudaSuccess) return -1;
+    // A band is complete when its flag holds the generation of the current launch; whatever an
+    // earlier launch (or an earlier plan that owned this memory) left there does not match, so
+    // the poll needs no ordering against the reset that the launch enqueues on the caller's stream.
+    if (cudaMemcpyAsync(pl->h_flags.data(), pl->d_band_flag, (size_t)pl->nbands * sizeof(unsigned int),
+                        cudaMemcpyDeviceToHost, pl->side) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(pl->side) != cudaSuccess) return -1;
     int done = 0;
-    for (int i = 0; i < pl->nbands; ++i) done += flags_host[i] != 0;
+    const unsigned int gen = pl->gen;
+    for (int i = 0; i < pl->nbands; ++i) { const int c = gen != 0 && pl->h_flags[i] == gen; flags_host[i] = (unsigned char)c; done += c; }
     return done;
 }
 

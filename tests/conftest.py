@@ -9,6 +9,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
+# Test hook of libmdzcuda (mdzcuda.cu, mdzcuda_plan_launch): every launch first fills its
+# iteration buffer with 0x7f7f7f7f, so a band handed to the host before the kernel has
+# completed it is a deterministic mismatch instead of plausible stale data.
+os.environ.setdefault("MDZCUDA_DEBUG_POISON", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

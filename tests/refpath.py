@@ -26,6 +26,12 @@ def load():
                                P, P, P, P, G, G, G, P, P,
                                C.c_int, C.c_void_p, C.POINTER(C.c_double)]
     lib.ref_render.restype = C.c_int
+    if hasattr(lib, "ref_render_lines"):
+        lib.ref_render_lines.argtypes = [C.c_int, C.c_long, C.c_int, C.c_int, C.c_long,
+                                         C.c_int, C.c_int, C.c_int,
+                                         P, P, P, P, G, G, G, P, P,
+                                         C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.ref_render_lines.restype = C.c_int
     return lib
 
 
@@ -45,3 +51,23 @@ def ref_render(lib, view, threads=None):
                         threads, out.ctypes.data_as(C.c_void_p), C.byref(secs))
     assert ok == 1
     return out, secs.value
+
+
+def ref_render_lines(lib, view, lines, threads=None):
+    """The reference's own line driver on selected real lines of a view of any size
+    -> int32 [len(lines)][real_width] (oracle/ref_driver.c: ref_render_lines)."""
+    threads = threads or os.cpu_count() or 2
+    lines = np.ascontiguousarray(np.asarray(lines, dtype=np.int32))
+    out = np.full((len(lines), view.real_width), -1, dtype=np.int32)
+
+    def p(v):
+        return v.ptr if v is not None else None
+    ok = lib.ref_render_lines(view.mode, view.precision, view.family, view.fractal, view.depth,
+                              view.user_width, view.user_height, view.aa_factor,
+                              p(view.xmin), p(view.xmax), p(view.ymax), p(view.width),
+                              p(view.gxmin), p(view.gymax), p(view.gwidth),
+                              p(view.julia_re), p(view.julia_im),
+                              lines.ctypes.data_as(C.c_void_p), len(lines), threads,
+                              out.ctypes.data_as(C.c_void_p))
+    assert ok == 1
+    return out

@@ -191,3 +191,25 @@ def test_cycle_detection_changes_nothing(ref_lib, name, mk):
         bad = np.argwhere(got != want)
         assert bad.size == 0, "%s spec=%d: %d mismatching pixels, first %s: got %d want %d" % (
             name, spec, len(bad), bad[0], got[tuple(bad[0])], want[tuple(bad[0])])
+
+
+def test_delivery_never_runs_ahead_of_the_kernel(ref_lib):
+    """Regression: band flags left in recycled memory (by an earlier plan, or by the same
+    plan's previous launch) must not be mistaken for this launch's -- once per ~300 strided
+    renders a frame used to be delivered before it was rendered.  Flags now carry the launch
+    generation; with the poison hook (conftest.py) an early delivery cannot go unnoticed."""
+    v = make_view("-0.743", "0.131", "0.02", 640, 360, precision=128, depth=3000)
+    want, _ = ref_render(ref_lib, v)
+    p = mdz_b200.Plan(v, 0)
+    for rep in range(6):                       # relaunching one plan: its own flags are stale each time
+        assert np.array_equal(p.run(), want), rep
+        assert p.bands_done() == p.bands_total()
+    p.close()
+    for rep in range(60):                      # plan after plan on recycled buffers, strided
+        first = rep % 2
+        out = np.full_like(want, -1)
+        q = mdz_b200.Plan(v, 0, first, 2)
+        q.run(out)
+        q.close()
+        assert np.array_equal(out[first::2], want[first::2]), rep
+        assert (out[1 - first::2] == -1).all()

@@ -65,3 +65,20 @@ HONEYTRACE = ("-7.66701995256949964922178305994168934712886433081717606e-1",
 
 def honeytrace(w=96, h=72, depth=25000):
     return make_view(HONEYTRACE[0], HONEYTRACE[1], HONEYTRACE[2], w, h, precision=176, depth=depth)
+
+
+# BASELINE configs[3] "synthetic 1e-120 deep zoom": the Misiurewicz point M(23,2) of the
+# seahorse valley to 150 digits (tests/golden/make_deep_center.py); every pixel of a
+# 1e-120 wide view escapes after ~12 800 iterations
+DEEP120 = ("-0.77661059259970185656403950255299474932817032143986600096924365785204686090459870878696142803205041429132937443851811918717130866762136492225227431666272",
+           "0.13460896167502816605673727023305780954118749622040361733997923275543996926182434686374673753720867571346542156176411558667716488800448659989231766107654")
+
+
+def config4(w=3840, h=2160, depth=100000, mode="gmp", precision=512):
+    return make_view(DEEP120[0], DEEP120[1], "1e-120", w, h, mode=mode, precision=precision, depth=depth)
+
+
+# BASELINE configs[4]: Burning Ship / generalized Celtic, 7680x4320 with 3x3 anti-aliasing
+def config5(fractal, w=7680, h=4320, aa=3, depth=1000, mode="ld", precision=64):
+    cy = "-0.5" if fractal == BURNING_SHIP else "0.0"
+    return make_view("-0.5", cy, "4.0", w, h, mode=mode, precision=precision, depth=depth, aa=aa, fractal=fractal)
