@@ -68,6 +68,7 @@ struct DevPool {
     std::vector<cudaStream_t> streams;
     std::vector<cudaEvent_t> events;
     std::vector<unsigned int*> pinned;              // 16-word pinned staging chunks
+    std::multimap<size_t, void*> pinned_bufs;       // larger pinned staging buffers (table uploads), by capacity
 };
 constexpr int kMaxDev = 64;
 DevPool g_pool[kMaxDev];
@@ -180,6 +181,26 @@ cudaError_t pool_pinned(int dev, unsigned int** out)
     if (e == cudaSuccess) memset(*out, 0, 64);
     return e;
 }
+// pinned staging buffer of at least `bytes` (the H2D image of a plan's tables)
+cudaError_t pool_pinned_buf(int dev, void** out, size_t* cap, size_t bytes)
+{
+    DevPool& P = g_pool[dev];
+    const size_t want = (bytes + 65535) / 65536 * 65536;
+    {
+        std::lock_guard<std::mutex> lock(P.mu);
+        auto it = P.pinned_bufs.lower_bound(want);
+        if (it != P.pinned_bufs.end()) { *out = it->second; *cap = it->first; P.pinned_bufs.erase(it); return cudaSuccess; }
+    }
+    *cap = want;
+    return cudaMallocHost(out, want);
+}
+void pool_pinned_buf_free(int dev, void* ptr, size_t cap)
+{
+    if (!ptr) return;
+    DevPool& P = g_pool[dev];
+    std::lock_guard<std::mutex> lock(P.mu);
+    P.pinned_bufs.insert(std::make_pair(cap, ptr));
+}
 }  // namespace
 
 extern "C" void mdzcuda_trim(void)
@@ -188,19 +209,22 @@ extern "C" void mdzcuda_trim(void)
     if (cudaGetDeviceCount(&n) != cudaSuccess) return;
     for (int dev = 0; dev < n && dev < kMaxDev; ++dev) {
         DevPool& P = g_pool[dev];
-        std::vector<void*> drop; std::vector<cudaStream_t> ss; std::vector<cudaEvent_t> es; std::vector<unsigned int*> ps;
+        std::vector<void*> drop, hostbufs; std::vector<cudaStream_t> ss; std::vector<cudaEvent_t> es; std::vector<unsigned int*> ps;
         {
             std::lock_guard<std::mutex> lock(P.mu);
             for (auto& kv : P.free_blocks) drop.push_back(kv.second);
             P.free_blocks.clear(); P.cached = 0;
             ss.swap(P.streams); es.swap(P.events); ps.swap(P.pinned);
+            for (auto& kv : P.pinned_bufs) hostbufs.push_back(kv.second);
+            P.pinned_bufs.clear();
         }
-        if (drop.empty() && ss.empty() && es.empty() && ps.empty()) continue;
+        if (drop.empty() && ss.empty() && es.empty() && ps.empty() && hostbufs.empty()) continue;
         if (cudaSetDevice(dev) != cudaSuccess) continue;
         for (void* q : drop) cudaFree(q);
         for (auto s : ss) cudaStreamDestroy(s);
         for (auto e : es) cudaEventDestroy(e);
         for (auto q : ps) cudaFreeHost(q);
+        for (auto q : hostbufs) cudaFreeHost(q);
     }
 }
 
@@ -552,6 +576,7 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
     { const char* e = getenv("MDZCUDA_CYCLE_DETECT"); pl->cycle = (e && *e && *e != '0') ? 1 : 0; }
     pl->rc = make_round_cfg(n32, v->mode == MDZCUDA_MODE_LD ? 64 : (gmp ? 32 * n32 : (int)v->precision));
 
+    std::vector<uint32_t> table_image; size_t table_bytes = 0;
     HostTable xs, ys, jc;
     int ok = (v->mode == MDZCUDA_MODE_LD) ? prologue_ld(v, pl->line_map, xs, ys, jc)
            : gmp ? prologue_gmp(v, pl->line_map, xs, ys, jc, n32)
@@ -571,7 +596,7 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
             const size_t o_flag = ar.reserve((size_t)pl->nbands + 1);
             const size_t o_cancel = ar.reserve(4);
             CUDA_OKP(pool_alloc(device, (void**)&pl->d_arena, ar.words * sizeof(uint32_t)));
-            CUDA_OKP(cudaMemcpy(pl->d_arena, ar.host.data(), table_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            table_image.swap(ar.host); table_bytes = table_words * sizeof(uint32_t);
             uint32_t* b = pl->d_arena;
             pl->xs.m = b + o[0]; pl->xs.e = (int32_t*)(b + o[1]); pl->xs.s = b + o[2]; pl->xs.count = xs.count;
             pl->ys.m = b + o[3]; pl->ys.e = (int32_t*)(b + o[4]); pl->ys.s = b + o[5]; pl->ys.count = ys.count;
@@ -592,7 +617,16 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
         // stream could still be queued when the first poll reads them -- seen once per ~300
         // strided renders as a frame delivered before it was rendered).
         CUDA_OKP(cudaMemsetAsync(pl->d_ctrl, 0, pl->zero_words * sizeof(uint32_t), pl->side));
-        CUDA_OKP(cudaStreamSynchronize(pl->side));
+        {
+            // the tables go up from pinned staging (pooled: cudaMallocHost costs a millisecond)
+            void* stage = nullptr; size_t cap = 0;
+            CUDA_OKP(pool_pinned_buf(device, &stage, &cap, table_bytes));
+            memcpy(stage, table_image.data(), table_bytes);
+            cudaError_t e1 = cudaMemcpyAsync(pl->d_arena, stage, table_bytes, cudaMemcpyHostToDevice, pl->side);
+            cudaError_t e2 = cudaStreamSynchronize(pl->side);
+            pool_pinned_buf_free(device, stage, cap);
+            CUDA_OKP(e1); CUDA_OKP(e2);
+        }
         pl->h_flags.assign((size_t)pl->nbands + 1, 0u);
         CUDA_OKP(pool_event(device, &pl->done_ev));
         CUDA_OKP(pool_pinned(device, &pl->h_pinned));                    // staging words for progress / cancel traffic
