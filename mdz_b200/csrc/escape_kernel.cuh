@@ -152,7 +152,9 @@ escape_mpfr_kernel(const EscapeParams p)
     int finished_band = -1;
     bool exhausted = false;         // warp-uniform
     CycleState cyc; cyc.f0 = 0; cyc.f1 = 0; cyc.next = 0x7fffffff;
-    bool use_spec = SpecLimbs<N>::value && p.spec != 0;     // warp-uniform
+    // warp-uniform: 0 general step, 1 speculative, 2 speculative with wide-gap additions
+    // (p.spec: 0 off, 1 adaptive; 2 / 3 pin level 1 / 2 for A/B measurements)
+    int spec_level = (SpecLimbs<N>::value && p.spec != 0) ? (p.spec == 3 ? 2 : 1) : 0;
     int spec_pause = 0, spec_backoff = 8;
     unsigned pix = 0;
 
@@ -199,8 +201,9 @@ escape_mpfr_kernel(const EscapeParams p)
 
         // ---- iterate ------------------------------------------------------
         uint32_t rare_seen = 0;
+        int warp_steps = 0, warp_fell = 0;       // iterations of this chunk, and those in which some lane fell back
         bool event_loop = false;
-        if constexpr (N == 2) event_loop = use_spec;
+        if constexpr (N == 2) event_loop = spec_level != 0;
         if (event_loop) {
             // Long double mode (ld64_step.cuh).  The iteration is one branch-free block that
             // every lane runs, finished lanes included (their results are ignored); the warp
@@ -214,7 +217,9 @@ escape_mpfr_kernel(const EscapeParams p)
                     bool esc = pixel_step_spec<2>(nx, cre_m, cim_m, scr, p.rc, abs_im, abs_re, rare);
                     const bool cyc_ev = CYC && ((nx.wre.m[0] == cyc.f0 && nx.wim.m[0] == cyc.f1) || nx.iter == cyc.next);
                     const bool ev = active && (rare != 0 || esc || nx.iter >= p.depth || cyc_ev);
+                    warp_steps += 1;
                     if (!__any_sync(0xffffffffu, ev)) { st = nx; continue; }
+                    warp_fell += __any_sync(0xffffffffu, active && rare != 0) ? 1 : 0;
                     if (active) {
                         if (rare != 0) { rare_seen += 1; esc = pixel_step<2>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re); }
                         else st = nx;
@@ -238,10 +243,11 @@ escape_mpfr_kernel(const EscapeParams p)
             }
         } else
         for (int k = 0; k < p.chunk; ++k) {
+            const uint32_t rare_before = rare_seen;
             if (active) {
                 bool esc;
                 if (SpecLimbs<N>::value)
-                    esc = pixel_step_auto<N, SpecSmemCkpt<N>::value>(st, cre_m, cim_m, scr, ckpt, p.rc, abs_im, abs_re, use_spec, rare_seen);
+                    esc = pixel_step_auto<N, SpecSmemCkpt<N>::value>(st, cre_m, cim_m, scr, ckpt, p.rc, abs_im, abs_re, spec_level, rare_seen);
                 else
                     esc = pixel_step<N>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re);
                 const int iter = st.iter;
@@ -259,23 +265,34 @@ escape_mpfr_kernel(const EscapeParams p)
                     if (done == (unsigned)p.width * (unsigned)p.aa) finished_band = (int)band;
                 }
             }
+            // one lane falling back makes the whole warp wait for the general step
+            if (SpecLimbs<N>::value && spec_level != 0) {
+                warp_steps += 1;
+                warp_fell += __any_sync(0xffffffffu, rare_seen != rare_before) ? 1 : 0;
+            }
             // a lane that completed a band hands it to the whole warp: colour it (fused
             // epilogue), then publish the band flag the host polls
             if (publish_bands(p, finished_band, lane)) finished_band = -1;
             if (!__any_sync(0xffffffffu, active)) break;
         }
         // ---- adapt: speculation is only worth it while fall-backs are scarce ----
-        if (SpecLimbs<N>::value) {
-            if (use_spec) {
-                // a lane that fell back in at least a quarter of the chunk votes against
-                const unsigned against = __popc(__ballot_sync(0xffffffffu, rare_seen * 4u >= (unsigned)p.chunk));
-                if (against * 4u >= 32u) {      // back off exponentially: 16, 32, ... 4096 chunks
-                    use_spec = false;
+        // One lane that falls back makes its whole warp run the general step as well, and an
+        // event that a lane meets once in thirty iterations a warp meets in most of them.  So the
+        // measure is the warp's: when more than a quarter of a chunk's iterations had a fall-back,
+        // level 1 (gaps below 31 bits) gives way to level 2 (gaps up to 126 bits, cancellation up
+        // to 62 bits, ~5N instructions more per addition), and level 2 to the general step, each for
+        // an exponentially growing number of chunks (16 ... 4096) before the cheaper one is retried.
+        if (SpecLimbs<N>::value && p.spec == 1) {
+            if (spec_level != 0) {
+                if (warp_fell * 4 > warp_steps) {
                     spec_backoff = spec_backoff < 4096 ? spec_backoff * 2 : 4096;
                     spec_pause = spec_backoff;
-                } else if (against == 0) spec_backoff = 8;
+                    spec_level = (spec_level == 1 && N > 2) ? 2 : 0;
+                } else if (spec_level == 2) {
+                    if (--spec_pause <= 0) spec_level = 1;          // see whether the narrow one will do again
+                } else if (warp_fell == 0) spec_backoff = 8;
             } else if (--spec_pause <= 0) {
-                use_spec = p.spec != 0;
+                spec_level = 1;
             }
         }
     }

@@ -116,6 +116,41 @@ MDZ_HD bool pixel_step_spec(PixelState<N>& st, const uint32_t* cre_m, const uint
     return esc;
 }
 
+// The same step with fadd_spec_wide (gaps up to 126 bits): level 2 of pixel_step_auto.
+template <int N>
+MDZ_HD bool pixel_step_spec_wide(PixelState<N>& st, const uint32_t* cre_m, const uint32_t* cim_m,
+                            uint32_t* scr, const RoundCfg& rc, bool abs_im, int abs_re, uint32_t& rare)
+{
+    ++st.iter;
+    Num<N> t, u, c, c2;
+    MDZ_UNROLL
+    for (int q = 0; q < N; ++q) c.m[q] = cim_m[q * kScratchStride];
+    c.e = st.cim_e; c.s = st.cim_s;
+    MDZ_UNROLL
+    for (int q = 0; q < N; ++q) c2.m[q] = cre_m[q * kScratchStride];
+    c2.e = st.cre_e; c2.s = st.cre_s;
+    fmul_spec<N>(st.wre, st.wim, t, rc, rare);
+    fadd_spec_wide<N, MODE_SUB_POS>(st.wre2, st.wim2, u, rc, rare);
+    if (abs_re == 1 || (abs_re == 2 && (st.iter & 1))) u.s = 0;
+    fadd_spec_wide<N, MODE_GENERIC>(u, c2, st.wre, rc, rare);
+    if (t.m[N - 1] != 0) t.e += 1;
+    if (abs_im) t.s = 0;
+    fadd_spec_wide<N, MODE_GENERIC>(t, c, st.wim, rc, rare);
+    fsqr_spec<N>(st.wre, st.wre2, rc, rare);
+    fsqr_spec<N>(st.wim, st.wim2, rc, rare);
+    const int32_t emax = st.wim2.e > st.wre2.e ? st.wim2.e : st.wre2.e;
+    bool esc = emax >= 4;
+    if (rare == 0 && !esc && emax >= 2) {
+        MDZ_COUNT(CNT_ESC_ADD);
+        uint32_t r2 = 0;
+        fadd_spec_wide<N, MODE_ADD_POS>(st.wim2, st.wre2, t, rc, r2);
+        if (r2 != 0) fadd<N, MODE_ADD_POS>(st.wim2, st.wre2, t, rc, scr);
+        esc = greater_than_4<N>(t);
+    }
+    return esc;
+}
+
+
 // Checkpoint of the loop-carried state for the speculative step.  For small limb
 // counts it simply stays in registers; for large ones (4N extra registers would cost a
 // resident block) it goes to a per-thread shared-memory column of 4N+5 words.
@@ -166,13 +201,15 @@ MDZ_HD void ckpt_load(PixelState<N>& st, const uint32_t* ck)
 template <int N, bool SMEM_CKPT>
 MDZ_HD bool pixel_step_auto(PixelState<N>& st, const uint32_t* cre_m, const uint32_t* cim_m,
                             uint32_t* scr, uint32_t* ckpt, const RoundCfg& rc, bool abs_im, int abs_re,
-                            bool use_spec, uint32_t& rare_seen)
+                            int level, uint32_t& rare_seen)
 {
-    if (use_spec) {
+    // level: 0 general step only, 1 speculative, 2 speculative with the wide-gap additions
+    if (level != 0) {
         PixelState<N> keep;
         if (SMEM_CKPT) ckpt_save<N>(st, ckpt); else keep = st;
         uint32_t rare = 0;
-        const bool esc = pixel_step_spec<N>(st, cre_m, cim_m, scr, rc, abs_im, abs_re, rare);
+        const bool esc = level == 2 ? pixel_step_spec_wide<N>(st, cre_m, cim_m, scr, rc, abs_im, abs_re, rare)
+                                    : pixel_step_spec<N>(st, cre_m, cim_m, scr, rc, abs_im, abs_re, rare);
         if (rare == 0) return esc;
         MDZ_COUNT(CNT_SPEC_FALLBACK);
         rare_seen += 1;

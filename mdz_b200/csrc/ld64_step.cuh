@@ -153,4 +153,12 @@ MDZ_HD bool pixel_step_spec<2>(PixelState<2>& st, const uint32_t* cre_m, const u
     return esc;
 }
 
+// two limbs have no separate wide variant: the step above already covers gaps up to 62 bits
+template <>
+MDZ_HD bool pixel_step_spec_wide<2>(PixelState<2>& st, const uint32_t* cre_m, const uint32_t* cim_m,
+                                    uint32_t* scr, const RoundCfg& rc, bool abs_im, int abs_re, uint32_t& rare_out)
+{
+    return pixel_step_spec<2>(st, cre_m, cim_m, scr, rc, abs_im, abs_re, rare_out);
+}
+
 }  // namespace mdz

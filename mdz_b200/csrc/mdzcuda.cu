@@ -698,6 +698,7 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         p.fractal = pl->view.fractal;
         p.chunk = pl->chunk ? pl->chunk : default_chunk(pl->n32);
         p.spec = pl->spec;
+        if (p.spec == 1) { static const int forced = [] { const char* e = getenv("MDZCUDA_SPEC_LEVEL"); return e && *e ? atoi(e) : 1; }(); p.spec = forced; }   // A/B: 2 / 3 pin level 1 / 2
         p.colour = pl->colour;
         const int cyc = (pl->cycle && !pl->gmp) ? 1 : 0;
         kernel_fn fn = pl->gmp ? gmp_kernel_for_limbs(pl->n32 / 2) : kernel_for_limbs(pl->n32, cyc);

@@ -444,6 +444,102 @@ MDZ_HD void fadd_spec(const Num<N>& a, const Num<N>& b, Num<N>& r, const RoundCf
     r.s = s;
 }
 
+// Wide-gap variant: exponent gaps up to 126 bits (three whole limbs plus 30 bits), still
+// branch-free.  The operands are first ordered by exponent (selects), so only the smaller
+// one goes through the shifter -- two conditional limb moves (by one and by two limbs) and a
+// funnel shift -- and only it is complemented for a subtraction; what falls off the guard
+// limb is the sticky bit, which enters the difference as a borrow exactly as in fadd.  About
+// 3N+1 instructions more per addition than fadd_spec, so the kernel switches to it per warp,
+// when orbits keep meeting gaps of 31 bits and more (views hugging an axis: in
+// gallery/deep_embedded_julia.mdz wre^2 - wim^2 has a 31..40-bit gap every other iteration).
+template <int N, int MODE>
+MDZ_HD void fadd_spec_wide(const Num<N>& a, const Num<N>& b, Num<N>& r, const RoundCfg& rc, uint32_t& rare)
+{
+    const uint32_t sb = (MODE == MODE_SUB_POS) ? 1u : (MODE == MODE_ADD_POS ? 0u : b.s);
+    const uint32_t sa = (MODE == MODE_GENERIC) ? a.s : 0u;
+    const bool sub = (MODE == MODE_SUB_POS) ? true : (MODE == MODE_ADD_POS ? false : (sa != sb));
+    const int32_t d = a.e - b.e;
+    const uint32_t ad = (uint32_t)(d < 0 ? -d : d);
+    rare |= (ad > 126u) ? 1u : 0u;
+    if (ad > 126u) MDZ_COUNT(CNT_SPEC_GAP);
+    // order by magnitude: exponent, then the whole significand (one borrow chain), so that a
+    // difference is never negative -- also when the top limbs are equal
+    bool a_big = d >= 0;
+    if (MODE != MODE_ADD_POS) {
+        (void)sub_cc(a.m[0], b.m[0]);
+        MDZ_UNROLL
+        for (int i = 1; i < N; ++i) (void)subc_cc(a.m[i], b.m[i]);
+        const bool a_ge_b = subc(0u, 0u) == 0u;
+        a_big = d > 0 || (d == 0 && a_ge_b);
+    }
+    uint32_t big[N], y[N + 1];
+    MDZ_UNROLL
+    for (int i = 0; i < N; ++i) { big[i] = a_big ? a.m[i] : b.m[i]; y[i + 1] = a_big ? b.m[i] : a.m[i]; }
+    y[0] = 0u;                                       // guard limb
+    const int32_t e_big = a_big ? a.e : b.e;
+    const uint32_t s_big = a_big ? sa : sb;
+    // small >>= 32*q + rr, with sh = ad + 1 (one bit of headroom, as for the big one)
+    const uint32_t sh = ad + 1u, q = sh >> 5, rr = sh & 31u;
+    uint32_t sticky = 0;
+    {
+        const bool q1 = (q & 1u) != 0;               // by one limb: drops the (empty) guard
+        MDZ_UNROLL
+        for (int i = 0; i < N; ++i) y[i] = q1 ? y[i + 1] : y[i];
+        y[N] = q1 ? 0u : y[N];
+        const bool q2 = (q & 2u) != 0;               // by two limbs
+        sticky = q2 ? (y[0] | y[1]) : 0u;
+        MDZ_UNROLL
+        for (int i = 0; i + 2 <= N; ++i) y[i] = q2 ? y[i + 2] : y[i];
+        if (N >= 1) y[N - 1] = q2 ? 0u : y[N - 1];
+        y[N] = q2 ? 0u : y[N];
+    }
+    sticky |= fsr(0u, y[0], rr);                     // the bits of y[0] that the funnel shift drops
+    uint32_t xs[N + 1], xb[N + 1];
+    MDZ_UNROLL
+    for (int i = 0; i < N; ++i) xs[i] = fsr(y[i], y[i + 1], rr);
+    xs[N] = y[N] >> rr;
+    xb[0] = big[0] << 31;
+    MDZ_UNROLL
+    for (int i = 1; i < N; ++i) xb[i] = fsr(big[i - 1], big[i], 1u);
+    xb[N] = big[N - 1] >> 1;
+    sticky = sticky != 0 ? 1u : 0u;
+    uint32_t x[N + 1];
+    if (MODE == MODE_ADD_POS) {
+        x[0] = add_cc(xb[0], xs[0]);
+        MDZ_UNROLL
+        for (int i = 1; i < N; ++i) x[i] = addc_cc(xb[i], xs[i]);
+        x[N] = addc(xb[N], xs[N]);
+    } else {
+        const uint32_t ms = sub ? 0xffffffffu : 0u;
+        // big - small - sticky == big + ~small + (1 - sticky)
+        (void)add_cc(sub ? (sticky ^ 1u) : 0u, 0xffffffffu);
+        MDZ_UNROLL
+        for (int i = 0; i < N; ++i) x[i] = addc_cc(xb[i], xs[i] ^ ms);
+        x[N] = addc(xb[N], xs[N] ^ ms);
+    }
+    int32_t e_out = e_big + 1;
+    if (MODE != MODE_ADD_POS) {
+        // 31..62 cancelled bits (exact: the gap is at most one bit, nothing was dropped):
+        // move up one limb, by selects.  Deeper cancellation or an exact zero stays rare.
+        const bool z = x[N] == 0;
+        MDZ_UNROLL
+        for (int i = N; i >= 1; --i) x[i] = z ? x[i - 1] : x[i];
+        x[0] = z ? 0u : x[0];
+        e_out -= z ? 32 : 0;
+        rare |= (x[N] == 0) ? 1u : 0u;
+        if (x[N] == 0) MDZ_COUNT(CNT_SPEC_CANCEL);
+    }
+    const uint32_t lz = (uint32_t)clz32(x[N]);
+    MDZ_UNROLL
+    for (int i = N; i >= 1; --i) x[i] = fsl(x[i - 1], x[i], lz);
+    x[0] <<= lz;
+    rare |= round_rn_fast<N>(x, sticky, rc) ? 1u : 0u;
+    MDZ_UNROLL
+    for (int i = 0; i < N; ++i) r.m[i] = x[i + 1];
+    r.e = e_out - (int32_t)lz;
+    r.s = s_big;
+}
+
 template <int N>
 MDZ_HD void fmul_spec(const Num<N>& a, const Num<N>& b, Num<N>& r, const RoundCfg& rc, uint32_t& rare)
 {

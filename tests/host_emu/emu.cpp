@@ -31,6 +31,15 @@ static int binop(int op, long prec,
     case 4: fadd<N, MODE_SUB_POS>(a, b, r, rc, scratch); break;
     case 5: fadd<N, MODE_ADD_POS>(a, b, r, rc, scratch); break;
     case 6: *rs = greater_than_4<N>(a) ? 1 : 0; return 1;
+    case 7: case 8: case 9: case 10: {      // fadd_spec_wide: add, sub, a-b with a,b >= 0, a+b with a,b >= 0; returns 2 when it declined
+        uint32_t rare = 0;
+        if (op == 8) b.s ^= 1u;
+        if (op == 7 || op == 8) fadd_spec_wide<N, MODE_GENERIC>(a, b, r, rc, rare);
+        else if (op == 9) fadd_spec_wide<N, MODE_SUB_POS>(a, b, r, rc, rare);
+        else fadd_spec_wide<N, MODE_ADD_POS>(a, b, r, rc, rare);
+        if (rare) return 2;
+        break;
+    }
     default: return 0;
     }
     if (is_zero(r)) { *rs = 0; *re = 0; for (int i = 0; i < limbs64_for_prec(prec); ++i) rl[i] = 0; return 1; }
@@ -90,8 +99,8 @@ static long pixel(long prec, int fractal, long depth, int spec,
     uint32_t rare_seen = 0;
     uint32_t ck[CkptWords<N>::value];
     while (st.iter < depth)
-        if (spec == 2 ? pixel_step_auto<N, true>(st, cre, cim, scr, ck, rc, abs_im, abs_re, true, rare_seen)
-                      : pixel_step_auto<N, false>(st, cre, cim, scr, ck, rc, abs_im, abs_re, spec != 0, rare_seen)) return st.iter;
+        if ((spec == 2 || spec == 4) ? pixel_step_auto<N, true>(st, cre, cim, scr, ck, rc, abs_im, abs_re, spec == 4 ? 2 : 1, rare_seen)
+                                     : pixel_step_auto<N, false>(st, cre, cim, scr, ck, rc, abs_im, abs_re, spec == 3 ? 2 : spec, rare_seen)) return st.iter;
     return 0;
 }
 

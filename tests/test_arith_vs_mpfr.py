@@ -223,3 +223,49 @@ def test_ld64_fast_ops_match_libmpfr_or_decline(emu):
             else:
                 assert (rs.value, re_.value, rm.value) == want, (name, a.parts(), b.parts(), want)
     assert declined[0] < 2500 and declined[2] < 12000 and declined[3] < 12000, declined
+
+
+# ---- the wide-gap speculative addition (mpfr_sf.cuh: fadd_spec_wide) ----------------------
+@pytest.mark.parametrize("prec", [80, 96, 128, 176, 256, 320, 511, 512])
+def test_wide_gap_speculative_add_matches_libmpfr_or_declines(emu, prec):
+    """fadd_spec_wide gives libmpfr's result or declines, and inside its domain (gap <= 126
+    bits, no zero operand, fewer than 63 cancelled bits) it may decline only for a rounding
+    carry out of the lowest limb."""
+    rng = random.Random(7000 + prec)
+    declined = covered_declines = 0
+    for k in range(4000):
+        a, b = rand_pair(rng, prec)
+        sa, ea, ma = a.parts()
+        sb, eb, mb = b.parts()
+        if k % 3 == 0 and sa and sb:             # medium gaps: the cases this variant exists for
+            eb = ea + rng.choice([-1, 1]) * rng.randrange(25, 131)
+            b = Mpfr(prec).set_parts(sb, eb, mb)
+        a2 = Mpfr(prec).set_parts(abs(sa), ea, ma)
+        b2 = Mpfr(prec).set_parts(abs(sb), eb, mb)
+        for op, name, x, y in ((7, "add", a, b), (8, "sub", a, b), (9, "sub", a2, b2), (10, "add", a2, b2)):
+            n = nlimbs64(prec)
+            al, bl = (C.c_uint64 * n)(*x.limbs()), (C.c_uint64 * n)(*y.limbs())
+            rl, rs, re_ = (C.c_uint64 * n)(), C.c_int(), C.c_long()
+            sx, ex, _ = x.parts()
+            sy, ey, _ = y.parts()
+            rc = emu.emu_binop(op, prec, al, sx, ex, bl, sy, ey, rl, C.byref(rs), C.byref(re_))
+            want = mpfr_op(name, prec, x, y)
+            if rc == 2:
+                declined += 1
+                R = 32 * ((prec + 31) // 32) - prec
+                top = lambda v: v.parts()[2] >> (prec - 32)
+                eff_sub = (name == "add") != (sx == sy)
+                inside = sx != 0 and sy != 0 and abs(ex - ey) <= 126 and want[0] != 0
+                if inside and eff_sub:
+                    inside = want[1] >= max(ex, ey) - 61
+                if inside:
+                    inside = ((want[2] << R) & 0xffffffff) != 0     # else: the increment may have left limb 0
+                covered_declines += inside
+                continue
+            assert rc == 1
+            full = 0
+            for i in range(n):
+                full |= rl[i] << (64 * i)
+            got = (0, 0, 0) if rs.value == 0 else (rs.value, re_.value, full >> (64 * n - prec))
+            assert got == want, (name, op, x.parts(), y.parts(), got, want)
+    assert covered_declines == 0, (declined, covered_declines)

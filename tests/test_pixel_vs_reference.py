@@ -73,7 +73,8 @@ CASES = [
 
 
 @pytest.mark.parametrize("name,mk,count", CASES, ids=[c[0] for c in CASES])
-@pytest.mark.parametrize("spec", [0, 1, 2], ids=["general", "speculative", "speculative-smem-checkpoint"])
+@pytest.mark.parametrize("spec", [0, 1, 2, 3, 4], ids=["general", "speculative", "speculative-smem-checkpoint",
+                                                  "speculative-wide", "speculative-wide-smem-checkpoint"])
 def test_pixels_match_reference(emu, ref_lib, name, mk, count, spec):
     view = mk()
     W, H = view.real_width, view.real_height
