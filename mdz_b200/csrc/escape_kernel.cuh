@@ -203,7 +203,7 @@ escape_mpfr_kernel(const EscapeParams p)
         uint32_t rare_seen = 0;
         int warp_steps = 0, warp_fell = 0;       // iterations of this chunk, and those in which some lane fell back
         bool event_loop = false;
-        if constexpr (N == 2) event_loop = spec_level != 0;
+        if constexpr (N == 2) event_loop = spec_level != 0 && p.rc.ulp == 1u;   // the 64-bit step needs p = 64 exactly
         if (event_loop) {
             // Long double mode (ld64_step.cuh).  The iteration is one branch-free block that
             // every lane runs, finished lanes included (their results are ignored); the warp
@@ -211,17 +211,31 @@ escape_mpfr_kernel(const EscapeParams p)
             // or met a case the fast step declines -- so an interior pixel's ten thousand
             // iterations cost one vote and one branch each on top of the arithmetic.
             if constexpr (N == 2) {
+                Num<2> cre, cim;                         // c stays in registers across the chunk
+                cim.m[0] = cim_m[0]; cim.m[1] = cim_m[kScratchStride]; cim.e = st.cim_e; cim.s = st.cim_s;
+                cre.m[0] = cre_m[0]; cre.m[1] = cre_m[kScratchStride]; cre.e = st.cre_e; cre.s = st.cre_s;
+                PixelState<2> nx;
                 for (int k = 0; k < p.chunk; ++k) {
-                    PixelState<2> nx = st;
-                    uint32_t rare = 0;
-                    bool esc = pixel_step_spec<2>(nx, cre_m, cim_m, scr, p.rc, abs_im, abs_re, rare);
-                    const bool cyc_ev = CYC && ((nx.wre.m[0] == cyc.f0 && nx.wim.m[0] == cyc.f1) || nx.iter == cyc.next);
-                    const bool ev = active && (rare != 0 || esc || nx.iter >= p.depth || cyc_ev);
+                    // two iterations per trip, st -> nx -> st, so that no state is copied back
+                    bool rare = false;
+                    bool esc = ld64_step(st, nx, cre, cim, scr, p.rc, abs_im, abs_re, rare);
+                    bool cyc_ev = CYC && ((nx.wre.m[0] == cyc.f0 && nx.wim.m[0] == cyc.f1) || nx.iter == cyc.next);
+                    bool ev = active && (rare || esc || nx.iter >= p.depth || cyc_ev);
                     warp_steps += 1;
-                    if (!__any_sync(0xffffffffu, ev)) { st = nx; continue; }
-                    warp_fell += __any_sync(0xffffffffu, active && rare != 0) ? 1 : 0;
+                    if (!__any_sync(0xffffffffu, ev)) {
+                        if (++k >= p.chunk) { st = nx; break; }
+                        rare = false;
+                        esc = ld64_step(nx, st, cre, cim, scr, p.rc, abs_im, abs_re, rare);
+                        cyc_ev = CYC && ((st.wre.m[0] == cyc.f0 && st.wim.m[0] == cyc.f1) || st.iter == cyc.next);
+                        ev = active && (rare || esc || st.iter >= p.depth || cyc_ev);
+                        warp_steps += 1;
+                        if (!__any_sync(0xffffffffu, ev)) continue;
+                        // event in the second half: present it to the handler as (old = st, new = nx)
+                        const PixelState<2> tmp = st; st = nx; nx = tmp;
+                    }
+                    warp_fell += __any_sync(0xffffffffu, active && rare) ? 1 : 0;
                     if (active) {
-                        if (rare != 0) { rare_seen += 1; esc = pixel_step<2>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re); }
+                        if (rare) { rare_seen += 1; esc = pixel_step<2>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re); }
                         else st = nx;
                         bool periodic = false;
                         if (CYC && !esc) {

@@ -117,39 +117,53 @@ MDZ_HD void add64_spec(const Num<2>& a, const Num<2>& b, Num<2>& r, bool& rare)
     r.s = swap ? b.s : a.s;
 }
 
-template <>
-MDZ_HD bool pixel_step_spec<2>(PixelState<2>& st, const uint32_t* cre_m, const uint32_t* cim_m,
-                               uint32_t* scr, const RoundCfg& rc, bool abs_im, int abs_re, uint32_t& rare_out)
+// One iteration from `in` to `out` (distinct objects: the kernel's hot loop ping-pongs
+// between two register sets instead of copying the state back), c passed by value so that it
+// can live in registers.  `rare` comes back true when the step declined; `out` is then garbage.
+MDZ_HD bool ld64_step(const PixelState<2>& in, PixelState<2>& out, const Num<2>& cre, const Num<2>& cim,
+                      uint32_t* scr, const RoundCfg& rc, bool abs_im, int abs_re, bool& rare)
 {
-    ++st.iter;
-    bool rare = rc.ulp != 1u;                        // precision below 64 bits: general code only
-    Num<2> cim, cre, t, u, nw;
-    cim.m[0] = cim_m[0]; cim.m[1] = cim_m[kScratchStride]; cim.e = st.cim_e; cim.s = st.cim_s;
-    cre.m[0] = cre_m[0]; cre.m[1] = cre_m[kScratchStride]; cre.e = st.cre_e; cre.s = st.cre_s;
+    out.iter = in.iter + 1;
+    out.cre_e = in.cre_e; out.cim_e = in.cim_e; out.cre_s = in.cre_s; out.cim_s = in.cim_s;
+    Num<2> t, u, nw;
     // wim = 2*wre*wim + c_im
-    mul64_spec(st.wre, st.wim, t, rare);
+    mul64_spec(in.wre, in.wim, t, rare);
     t.e += 1;
-    t.s = abs_im ? 0u : (st.wre.s ^ st.wim.s);
+    t.s = abs_im ? 0u : (in.wre.s ^ in.wim.s);
     // wre = wre2 - wim2 + c_re
-    nw = st.wim2; nw.s = 1u;
-    add64_spec(st.wre2, nw, u, rare);
-    if (abs_re == 1 || (abs_re == 2 && (st.iter & 1))) u.s = 0;
-    add64_spec(t, cim, st.wim, rare);
-    add64_spec(u, cre, st.wre, rare);
-    mul64_spec(st.wim, st.wim, st.wim2, rare);
-    mul64_spec(st.wre, st.wre, st.wre2, rare);
-    st.wim2.s = 0; st.wre2.s = 0;
-    rare_out |= rare ? 1u : 0u;
-    const int32_t emax = st.wim2.e > st.wre2.e ? st.wim2.e : st.wre2.e;
+    nw = in.wim2; nw.s = 1u;
+    add64_spec(in.wre2, nw, u, rare);
+    if (abs_re == 1 || (abs_re == 2 && (out.iter & 1))) u.s = 0;
+    add64_spec(t, cim, out.wim, rare);
+    add64_spec(u, cre, out.wre, rare);
+    mul64_spec(out.wim, out.wim, out.wim2, rare);
+    mul64_spec(out.wre, out.wre, out.wre2, rare);
+    out.wim2.s = 0; out.wre2.s = 0;
+    const int32_t emax = out.wim2.e > out.wre2.e ? out.wim2.e : out.wre2.e;
     bool esc = emax >= 4;
     if (!rare && !esc && emax >= 2) {
         // RN(wim2 + wre2) > 4 can only be in doubt when the larger square is in [2, 8)
         MDZ_COUNT(CNT_ESC_ADD);
         Num<2> sum; bool r2 = false;
-        add64_spec(st.wim2, st.wre2, sum, r2);
-        if (r2) fadd<2, MODE_ADD_POS>(st.wim2, st.wre2, sum, rc, scr);
+        add64_spec(out.wim2, out.wre2, sum, r2);
+        if (r2) fadd<2, MODE_ADD_POS>(out.wim2, out.wre2, sum, rc, scr);
         esc = greater_than_4<2>(sum);
     }
+    return esc;
+}
+
+template <>
+MDZ_HD bool pixel_step_spec<2>(PixelState<2>& st, const uint32_t* cre_m, const uint32_t* cim_m,
+                               uint32_t* scr, const RoundCfg& rc, bool abs_im, int abs_re, uint32_t& rare_out)
+{
+    bool rare = rc.ulp != 1u;                        // precision below 64 bits: general code only
+    Num<2> cim, cre;
+    cim.m[0] = cim_m[0]; cim.m[1] = cim_m[kScratchStride]; cim.e = st.cim_e; cim.s = st.cim_s;
+    cre.m[0] = cre_m[0]; cre.m[1] = cre_m[kScratchStride]; cre.e = st.cre_e; cre.s = st.cre_s;
+    PixelState<2> out;
+    const bool esc = ld64_step(st, out, cre, cim, scr, rc, abs_im, abs_re, rare);
+    st = out;
+    rare_out |= rare ? 1u : 0u;
     return esc;
 }
 
