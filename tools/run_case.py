@@ -23,6 +23,8 @@ def case(name, scale=1.0):
         if p == 320:
             return deep_embedded_julia(w, h)
         return make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", w, h, precision=p, depth=10000)
+    if name.startswith("gmp"):
+        return make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", w, h, mode="gmp", precision=int(name[3:]), depth=10000)
     if name.startswith("sea"):
         return make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", w, h, precision=int(name[3:]), depth=10000)
     if name.startswith("dej"):
