@@ -11,7 +11,7 @@ import time
 import numpy as np
 
 from . import Plan, device_count, last_error
-from .mdzfile import load_mdz, view_from_settings
+from .mdzfile import load_mdz, view_from_settings, settings_text
 from .png import write_png
 
 
@@ -73,6 +73,8 @@ def main(argv=None):
     write_png(a.render, rgb)
     if a.log_file:
         with (sys.stdout if a.log_file == "-" else open(a.log_file, "w")) as f:
+            # render.c:21-22 writes the settings block before the render, :98-102 the rest after it
+            f.write(settings_text(s, a.width, a.height, a.aspect_ratio))
             f.write("render-time %.3fs\nsaved-image %s\n" % (dt, a.render))
     return 0
 

@@ -45,6 +45,9 @@ class MdzSettings:
         self.pal_offset = 0
         self.palette = None       # list of packed R | G<<8 | B<<16 (palette.h:16)
         self.palette_file = None
+        # random-palette parameters (random_palette.h:20-31; defaults of image_info.c:290-299)
+        self.rnd = dict(r_strength=1.0, r_bands=0.05, g_strength=1.0, g_bands=0.08,
+                        b_strength=1.0, b_bands=0.2, offset=0, stripe=1, spread=1)
 
 
 def _clean(line):
@@ -133,6 +136,12 @@ def load_mdz(path):
     if s.family == FAMILY_JULIA:
         s.julia = (need("julia-real"), need("julia-imag"))
     s.pal_offset = int(kv.get("palette-offset", "0"))
+    for key, name, conv in (("r-strength", "r_strength", float), ("r-bands", "r_bands", float),
+                            ("g-strength", "g_strength", float), ("g-bands", "g_bands", float),
+                            ("b-strength", "b_strength", float), ("b-bands", "b_bands", float),
+                            ("rnd-offset", "offset", int), ("rnd-stripe", "stripe", int), ("rnd-spread", "spread", int)):
+        if key in kv:
+            s.rnd[name] = conv(kv[key])
     if pal_start is not None and pal_start < len(lines):
         if lines[pal_start] == "data":
             pal = []
@@ -213,3 +222,85 @@ def view_from_settings(s, width=None, height=None, aa=1, aspect_opt=0.0,
 
 def view_from_mdz(path, width=None, height=None, aa=1, **kw):
     return view_from_settings(load_mdz(path), width, height, aa, **kw)
+
+
+# ---------------------------------------------------------------------------
+# writer
+# ---------------------------------------------------------------------------
+FILE_HEADER = "mdz fractal settings"            # image_info.c:20
+VERSION = "0.1.2"                                # src/Makefile:1
+
+
+def settings_text(s, width=None, height=None, aspect_opt=0.0, bug_compatible=True, rect=None):
+    """The block image_info_save_settings writes (reference src/image_info.c:346-419) for
+    settings `s` as the cmdline path holds them after init_misc: what `mdz -l file -w W -h H
+    -L log` puts at the head of its log.  The centre and size are printed at the coords
+    precision with every digit (mpfr_out_str base 10, n = 0); the active reference (centre or
+    corners) is the uncommented one.  On the cmdline path the log is written before the first
+    coords_get_rect, so img->xmin/xmax/ymax are still NaN (render.c:21-22 precedes :34-37);
+    pass rect=(xmin, xmax, ymax) as Mpfr to write the values the GUI's save would."""
+    P = s.precision
+    cp = coords_precision(P)
+    w0 = DEFAULT_WIDTH
+    h0 = int(w0 / s.aspect)
+    aspect0 = float(w0) / h0
+    if s.center is not None:
+        cx, cy = Mpfr(cp, Mpfr(P, s.center[0])), Mpfr(cp, Mpfr(P, s.center[1]))
+        size = Mpfr(cp, Mpfr(P, s.center[2]))
+    else:
+        xmin, xmax, ymax = (Mpfr(cp, Mpfr(P, t)) for t in s.rect)
+        wd, ht, ymin, cx, cy = Mpfr(cp), Mpfr(cp), Mpfr(cp), Mpfr(cp), Mpfr(cp)
+        mpfr.mpfr_sub(wd.ref, xmax.ref, xmin.ref, 0)
+        mpfr.mpfr_div_d(ht.ref, wd.ref, aspect0, 0)
+        mpfr.mpfr_sub(ymin.ref, ymax.ref, ht.ref, 0)
+        mpfr.mpfr_add(cx.ref, xmin.ref, xmax.ref, 0)
+        mpfr.mpfr_div_ui(cx.ref, cx.ref, 2, 0)
+        mpfr.mpfr_add(cy.ref, ymin.ref, ymax.ref, 0)
+        mpfr.mpfr_div_ui(cy.ref, cy.ref, 2, 0)
+        size = Mpfr(cp, 4.0) if bug_compatible else (wd if aspect0 > 1.0 else ht)
+    if not width and not height:
+        width, height = w0, (int(w0 / aspect_opt) if aspect_opt else h0)
+    elif not width:
+        width = int(height * (aspect_opt if aspect_opt else aspect0))
+    elif not height:
+        height = int(width / (aspect_opt if aspect_opt else aspect0))
+    aspect = float(width) / height                                  # image_info_set (image_info.c:133)
+    center = "" if s.center is not None else "#"                    # img->ui_ref_center
+    corner = "#" if s.center is not None else ""
+    ip = max(P, 80)
+    r = rect if rect is not None else [Mpfr(ip).set_nan() for _ in range(3)]
+    yn = lambda b: "yes" if b else "no"
+    out = ["# http://jwm-art.net/mdz/", "settings",
+           "family %s" % FAMILY_STR[s.family], "fractal %s" % FRACTAL_STR[s.fractal],
+           "depth %d" % s.depth, "aspect %0.20f" % aspect, "colour-scale %0.20f" % s.colour_scale,
+           "colour-interpolate %s" % yn(s.palette_ip), "multi-precision %s" % yn(s.use_multi_prec),
+           "multi-rounding %s" % yn(s.use_rounding), "precision %d" % P,
+           "%scx %s" % (center, cx.out_str()), "%scy %s" % (center, cy.out_str()),
+           "%ssize %s" % (center, size.out_str()),
+           "%sxmin %s" % (corner, r[0].out_str()), "%sxmax %s" % (corner, r[1].out_str()),
+           "%symax %s" % (corner, r[2].out_str())]
+    if s.family == FAMILY_JULIA:
+        # image_info.c:703-704 / :271-272: c_re at the image precision, c_im keeps 80 bits
+        out.append("julia-real %s" % Mpfr(ip, Mpfr(P, s.julia[0])).out_str())
+        out.append("julia-imag %s" % Mpfr(ip if not bug_compatible else 80, Mpfr(P, s.julia[1])).out_str())
+    out.append("palette-offset %d" % s.pal_offset)
+    q = s.rnd
+    out += ["r-strength %f" % q["r_strength"], "r-bands %f" % q["r_bands"],
+            "g-strength %f" % q["g_strength"], "g-bands %f" % q["g_bands"],
+            "b-strength %f" % q["b_strength"], "b-bands %f" % q["b_bands"],
+            "rnd-offset %d" % q["offset"], "rnd-stripe %d" % q["stripe"], "rnd-spread %d" % q["spread"]]
+    return "\n".join(out) + "\n"
+
+
+def save_mdz(path, s, **kw):
+    """A complete settings file (image_info_f_save_all, image_info.c:323-343): header,
+    settings block, palette (embedded data or the file it came from)."""
+    text = "%s %s\n" % (FILE_HEADER, VERSION) + settings_text(s, **kw) + "palette\n"
+    if s.palette_file:
+        text += "file %s\n" % s.palette_file
+    else:
+        text += "data\n"
+        for c in (s.palette or []):
+            text += " %d %d %d\n" % (c & 0xff, (c >> 8) & 0xff, (c >> 16) & 0xff)      # palette_write, palette.c:190-203
+    with open(path, "w") as f:
+        f.write(text)

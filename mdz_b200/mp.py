@@ -48,6 +48,10 @@ mpfr.mpfr_get_version.restype = C.c_char_p
 mpfr.mpfr_get_str.argtypes = [C.c_char_p, C.POINTER(C.c_long), C.c_int, C.c_size_t, _P, C.c_int]
 mpfr.mpfr_get_str.restype = C.c_void_p
 mpfr.mpfr_free_str.argtypes = [C.c_void_p]
+mpfr.mpfr_free_str.restype = None
+mpfr.mpfr_set_nan.argtypes = [_P]
+mpfr.mpfr_set_nan.restype = None
+mpfr.mpfr_free_str.argtypes = [C.c_void_p]
 
 def _gf(name, argtypes, restype=None):
     fn = getattr(gmp, "__gmpf_" + name)     # exported names carry the __gmpf_ prefix
@@ -139,6 +143,26 @@ class Mpfr:
     def set_str(self, text, base=10):
         if mpfr.mpfr_set_str(self.ref, text.encode(), base, 0) != 0:
             raise ValueError("mpfr_set_str failed on %r" % text)
+        return self
+
+    def out_str(self):
+        """What mpfr_out_str(fd, 10, 0, x, GMP_RNDN) prints: all the digits needed to read the
+        value back exactly, one digit before the point, exponent always present."""
+        if self.s.exp == EXP_ZERO + 1:                     # NaN (mpfr.h: __MPFR_EXP_NAN)
+            return "@NaN@"
+        e = C.c_long()
+        raw = mpfr.mpfr_get_str(None, C.byref(e), 10, 0, self.ref, 0)
+        digits = C.cast(raw, C.c_char_p).value.decode()
+        mpfr.mpfr_free_str(C.c_void_p(raw))
+        sign = ""
+        if digits.startswith("-"):
+            sign, digits = "-", digits[1:]
+        if self.s.exp == EXP_ZERO:                          # zero: mpfr_get_str gives "0000..." with e = 0
+            return sign + digits[0] + "." + digits[1:] + "e0"
+        return "%s%s.%se%d" % (sign, digits[0], digits[1:], e.value - 1)
+
+    def set_nan(self):
+        mpfr.mpfr_set_nan(self.ref)
         return self
 
     def set_d(self, v):
