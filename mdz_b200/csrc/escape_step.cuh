@@ -40,6 +40,28 @@ MDZ_HD void pixel_init(PixelState<N>& st, const Num<N>& x, const Num<N>& y,
     st.iter = 0;
 }
 
+// RN(wim2 + wre2) > 4, the reference's bail-out test (mpfr_add + mpfr_greater_p,
+// src/frac_mandel.c:46-48).  Both squares below 2 cannot exceed 4 even after rounding,
+// either at 8 or more certainly does; in between the top limbs decide (escape_precheck)
+// unless the sum is within 2^-27 of 4, and only then is it formed.
+template <int N>
+MDZ_HD bool escaped(const Num<N>& wim2, const Num<N>& wre2, const RoundCfg& rc, uint32_t* scr)
+{
+    const int32_t emax = wim2.e > wre2.e ? wim2.e : wre2.e;
+    bool esc = emax >= 4;
+    if (!esc && emax >= 2) {
+        const int pre = escape_precheck<N>(wim2, wre2);
+        esc = pre > 0;
+        if (pre == 0) {
+            MDZ_COUNT(CNT_ESC_ADD);
+            Num<N> t;
+            fadd<N, MODE_ADD_POS>(wim2, wre2, t, rc, scr);
+            esc = greater_than_4<N>(t);
+        }
+    }
+    return esc;
+}
+
 // one iteration; returns true when RN(wim2 + wre2) > 4 (the pixel escaped at st.iter)
 template <int N>
 MDZ_HD bool pixel_step(PixelState<N>& st, const uint32_t* cre_m, const uint32_t* cim_m,
@@ -65,16 +87,7 @@ MDZ_HD bool pixel_step(PixelState<N>& st, const uint32_t* cre_m, const uint32_t*
     fadd<N, MODE_GENERIC>(t, c, st.wre, rc, scr);
     fsqr<N>(st.wim, st.wim2, rc);
     fsqr<N>(st.wre, st.wre2, rc);
-    // escape: RN(wim2 + wre2) > 4.  Both < 2 cannot exceed 4 even after
-    // rounding; either >= 8 certainly does.
-    const int32_t emax = st.wim2.e > st.wre2.e ? st.wim2.e : st.wre2.e;
-    bool esc = emax >= 4;
-    if (!esc && emax >= 2) {
-        MDZ_COUNT(CNT_ESC_ADD);
-        fadd<N, MODE_ADD_POS>(st.wim2, st.wre2, t, rc, scr);
-        esc = greater_than_4<N>(t);
-    }
-    return esc;
+    return escaped<N>(st.wim2, st.wre2, rc, scr);
 }
 
 
@@ -106,14 +119,7 @@ MDZ_HD bool pixel_step_spec(PixelState<N>& st, const uint32_t* cre_m, const uint
     fadd_spec<N, MODE_GENERIC>(t, c, st.wim, rc, rare);
     fsqr_spec<N>(st.wre, st.wre2, rc, rare);
     fsqr_spec<N>(st.wim, st.wim2, rc, rare);
-    const int32_t emax = st.wim2.e > st.wre2.e ? st.wim2.e : st.wre2.e;
-    bool esc = emax >= 4;
-    if (rare == 0 && !esc && emax >= 2) {
-        MDZ_COUNT(CNT_ESC_ADD);
-        fadd<N, MODE_ADD_POS>(st.wim2, st.wre2, t, rc, scr);
-        esc = greater_than_4<N>(t);
-    }
-    return esc;
+    return rare == 0 ? escaped<N>(st.wim2, st.wre2, rc, scr) : false;
 }
 
 // The same step with fadd_spec_wide (gaps up to 126 bits): level 2 of pixel_step_auto.
@@ -138,16 +144,7 @@ MDZ_HD bool pixel_step_spec_wide(PixelState<N>& st, const uint32_t* cre_m, const
     fadd_spec_wide<N, MODE_GENERIC>(t, c, st.wim, rc, rare);
     fsqr_spec<N>(st.wre, st.wre2, rc, rare);
     fsqr_spec<N>(st.wim, st.wim2, rc, rare);
-    const int32_t emax = st.wim2.e > st.wre2.e ? st.wim2.e : st.wre2.e;
-    bool esc = emax >= 4;
-    if (rare == 0 && !esc && emax >= 2) {
-        MDZ_COUNT(CNT_ESC_ADD);
-        uint32_t r2 = 0;
-        fadd_spec_wide<N, MODE_ADD_POS>(st.wim2, st.wre2, t, rc, r2);
-        if (r2 != 0) fadd<N, MODE_ADD_POS>(st.wim2, st.wre2, t, rc, scr);
-        esc = greater_than_4<N>(t);
-    }
-    return esc;
+    return rare == 0 ? escaped<N>(st.wim2, st.wre2, rc, scr) : false;
 }
 
 

@@ -142,12 +142,17 @@ MDZ_HD bool ld64_step(const PixelState<2>& in, PixelState<2>& out, const Num<2>&
     const int32_t emax = out.wim2.e > out.wre2.e ? out.wim2.e : out.wre2.e;
     bool esc = emax >= 4;
     if (!rare && !esc && emax >= 2) {
-        // RN(wim2 + wre2) > 4 can only be in doubt when the larger square is in [2, 8)
-        MDZ_COUNT(CNT_ESC_ADD);
-        Num<2> sum; bool r2 = false;
-        add64_spec(out.wim2, out.wre2, sum, r2);
-        if (r2) fadd<2, MODE_ADD_POS>(out.wim2, out.wre2, sum, rc, scr);
-        esc = greater_than_4<2>(sum);
+        // RN(wim2 + wre2) > 4 can only be in doubt when the larger square is in [2, 8), and
+        // then the top words settle it unless the sum is within 2^-27 of 4
+        const int pre = escape_precheck<2>(out.wim2, out.wre2);
+        esc = pre > 0;
+        if (pre == 0) {
+            MDZ_COUNT(CNT_ESC_ADD);
+            Num<2> sum; bool r2 = false;
+            add64_spec(out.wim2, out.wre2, sum, r2);
+            if (r2) fadd<2, MODE_ADD_POS>(out.wim2, out.wre2, sum, rc, scr);
+            esc = greater_than_4<2>(sum);
+        }
     }
     return esc;
 }

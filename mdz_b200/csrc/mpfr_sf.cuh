@@ -556,6 +556,25 @@ MDZ_HD void fsqr_spec(const Num<N>& a, Num<N>& r, const RoundCfg& rc, uint32_t& 
     rare |= finish_high<N>(t, a.e + a.e, 0u, r, rc) ? 1u : 0u;
 }
 
+// Escape test RN(a + b) > 4 for a, b >= 0 with exponents below 4, decided from the top limbs
+// where that is safe: in units of 2^-28 a value is less than floor(m_top * 2^(e-4)) + 1, so
+//   floors + 2 <= 2^30   ->  a + b < 4: no escape whatever the rounding;
+//   floors     >  2^30   ->  a + b >= 4 + 2^-28, which rounds above 4 at any precision >= 33;
+// returns -1 / +1 for those, 0 when the sum is within 2^-27 of 4 and has to be formed.
+// Orbits that hover just below |z|^2 = 4 (gallery/deep_embedded_julia.mdz spends three quarters
+// of its iterations with a square in [2, 4)) otherwise pay a fourth addition per iteration.
+template <int N>
+MDZ_HD int escape_precheck(const Num<N>& a, const Num<N>& b)
+{
+    const uint32_t sa = (uint32_t)(4 - a.e), sb = (uint32_t)(4 - b.e);       // >= 1 here
+    const uint32_t fa = sa < 32u ? a.m[N - 1] >> sa : 0u;
+    const uint32_t fb = sb < 32u ? b.m[N - 1] >> sb : 0u;
+    const uint32_t f = fa + fb;                                             // < 2^32: each is below 2^31
+    if (f <= (1u << 30) - 2u) return -1;
+    if (f > (1u << 30)) return 1;
+    return 0;
+}
+
 // a > 4 ?   (4 = 0.1b * 2^3)
 template <int N>
 MDZ_HD bool greater_than_4(const Num<N>& a)

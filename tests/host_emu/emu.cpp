@@ -31,6 +31,7 @@ static int binop(int op, long prec,
     case 4: fadd<N, MODE_SUB_POS>(a, b, r, rc, scratch); break;
     case 5: fadd<N, MODE_ADD_POS>(a, b, r, rc, scratch); break;
     case 6: *rs = greater_than_4<N>(a) ? 1 : 0; return 1;
+    case 11: { uint32_t scr2[ScratchWords<N>::value] = {0}; *rs = escaped<N>(a, b, rc, scr2) ? 1 : 0; return 1; }   // RN(a + b) > 4, a, b >= 0
     case 7: case 8: case 9: case 10: {      // fadd_spec_wide: add, sub, a-b with a,b >= 0, a+b with a,b >= 0; returns 2 when it declined
         uint32_t rare = 0;
         if (op == 8) b.s ^= 1u;

@@ -269,3 +269,34 @@ def test_wide_gap_speculative_add_matches_libmpfr_or_declines(emu, prec):
             got = (0, 0, 0) if rs.value == 0 else (rs.value, re_.value, full >> (64 * n - prec))
             assert got == want, (name, op, x.parts(), y.parts(), got, want)
     assert covered_declines == 0, (declined, covered_declines)
+
+
+@pytest.mark.parametrize("prec", [64, 80, 128, 320, 512])
+def test_escape_test_matches_mpfr_around_four(emu, prec):
+    """escaped(): RN(a + b) > 4 for squares a, b >= 0 -- decided from the top limbs unless the
+    sum is within 2^-27 of 4 (mpfr_sf.cuh: escape_precheck) -- against mpfr_add +
+    mpfr_greater_p, with sums crowded around 4 at every distance from 2^-(p+2) to 1."""
+    rng = random.Random(4000 + prec)
+    four = Mpfr(prec, 4)
+    n = nlimbs64(prec)
+    for k in range(6000):
+        # a in [0, 4), b = 4 - a + delta with |delta| from far below an ulp to O(1)
+        ea = rng.choice([3, 2, 2, 1, 0, -5, -40])
+        a = Mpfr(prec).set_parts(1, min(ea, 2) if ea == 3 else ea, rand_mant(rng, prec))
+        b = Mpfr(prec)
+        mpfr.mpfr_sub(b.ref, four.ref, a.ref, 0)
+        kind = k % 4
+        if kind != 0:
+            d = Mpfr(prec).set_parts(rng.choice([1, -1]), 3 - rng.randrange(0, prec + 3), rand_mant(rng, prec) if kind == 1 else 1 << (prec - 1))
+            mpfr.mpfr_add(b.ref, b.ref, d.ref, 0)
+        sb, eb, mb = b.parts()
+        if sb <= 0 or eb > 3:
+            continue
+        sa, ea2, _ = a.parts()
+        s = Mpfr(prec)
+        mpfr.mpfr_add(s.ref, a.ref, b.ref, 0)
+        want = 1 if mpfr.mpfr_greater_p(s.ref, four.ref) else 0
+        rs = C.c_int()
+        al, bl = (C.c_uint64 * n)(*a.limbs()), (C.c_uint64 * n)(*b.limbs())
+        emu.emu_binop(11, prec, al, sa, ea2, bl, sb, eb, (C.c_uint64 * n)(), C.byref(rs), C.byref(C.c_long()))
+        assert rs.value == want, (a.parts(), b.parts())
