@@ -376,6 +376,16 @@ MDZ_HD bool gf_pixel_step(GFPixel<NW>& st, const uint32_t* cre_m, const uint32_t
                        ? (gfz(st.wim2) ? -1000000 : st.wim2.e) : (gfz(st.wre2) ? -1000000 : st.wre2.e);
     if (emax >= 2) return true;
     if (emax <= 0) return false;
+    // emax == 1: a square with limb exponent 1 is its top limb plus a fraction below 1, so the
+    // integer parts bound the sum: ia + ib <= 2 -> below 4; >= 5 -> above 4 also after mpf_add's
+    // truncation.  Only 3 and 4 need the sum itself.
+    {
+        const bool ai = !gfz(st.wim2) && st.wim2.e == 1, bi = !gfz(st.wre2) && st.wre2.e == 1;
+        if ((ai && st.wim2.m[NW - 1] != 0) || (bi && st.wre2.m[NW - 1] != 0)) return true;     // >= 2^32
+        const uint64_t ip = (uint64_t)(ai ? st.wim2.m[NW - 2] : 0u) + (bi ? st.wre2.m[NW - 2] : 0u);
+        if (ip <= 2) return false;
+        if (ip >= 5) return true;
+    }
     gf_addsub<NW>(st.wim2, st.wre2, t1, false, scratch);
     return gf_gt4<NW>(t1);
 }
