@@ -10,7 +10,8 @@ import os
 from .mp import MpfrStruct, MpfStruct
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmdzcuda.so")
+# MDZCUDA_LIB: another build of the same library (A/B measurements of kernel variants, tools/)
+LIB_PATH = os.environ.get("MDZCUDA_LIB") or os.path.join(_HERE, "libmdzcuda.so")
 
 
 class MdzCudaError(RuntimeError):
@@ -80,6 +81,8 @@ def load():
             "Build it with __graft_entry__.build()." % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
+        if os.environ.get("MDZCUDA_LIB") and not hasattr(lib, name):
+            continue        # an older build under A/B comparison; the in-tree library must export everything
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

@@ -70,6 +70,22 @@ MDZ_HD bool pixel_step(PixelState<N>& st, const uint32_t* cre_m, const uint32_t*
     ++st.iter;
     MDZ_COUNT(CNT_ITER);
     Num<N> t, c;
+    // An orbit on the real axis stays there.  With wim == 0 and c_im == 0 the product wre*wim, its
+    // double and the sum with c_im are exact zeros, wim2 stays 0, and wre2 - 0 is wre2 with nothing to
+    // round (it is >= 0, so the |.| of the celtic variants changes nothing either): the nine calls of
+    // src/frac_mandel.c:36-48 produce wre = RN(wre2 + c_re), wre2 = RN(wre^2) and test wre2 alone.
+    // These are the pixels of the row y = 0, on which every product has a zero operand -- outside the
+    // fast iterations' domain, so each of them would otherwise pay the full general step, per lane,
+    // for up to `depth` iterations, and set the pace of its warp.
+    if (is_zero(st.wim) && cim_m[(N - 1) * kScratchStride] == 0u) {
+        MDZ_UNROLL
+        for (int q = 0; q < N; ++q) c.m[q] = cre_m[q * kScratchStride];
+        c.e = st.cre_e; c.s = st.cre_s;
+        t = st.wre2; t.s = 0;
+        fadd<N, MODE_GENERIC>(t, c, st.wre, rc, scr);
+        fsqr<N>(st.wre, st.wre2, rc);
+        return escaped<N>(st.wim2, st.wre2, rc, scr);
+    }
     // wim = 2*wre*wim + c_im       (|.| on the product for burning ship)
     fmul<N>(st.wre, st.wim, t, rc);
     if (t.m[N - 1] != 0) t.e += 1;

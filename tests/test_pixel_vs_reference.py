@@ -69,6 +69,11 @@ CASES = [
     ("celtic p96", lambda: make_view("-0.5", "-0.3", "3.5", 96, 72, precision=96, depth=300, fractal=GENERALIZED_CELTIC), 120),
     ("hybrid p184", lambda: make_view("-0.5", "-0.3", "3.5", 96, 72, precision=184, depth=300, fractal=VARIANT), 120),
     ("real axis p96", lambda: make_view("-0.75", "0.0", "2.5", 64, 48, precision=96, depth=500), 64),
+    # the row y = 0 takes the real-orbit shortcut of pixel_step (escape_step.cuh) in every fractal type
+    ("real axis p64", lambda: make_view("-0.75", "0.0", "2.5", 64, 48, precision=64, depth=2000), 64),
+    ("real axis ship p64", lambda: make_view("-0.5", "0.0", "3.5", 64, 48, precision=64, depth=500, fractal=BURNING_SHIP), 64),
+    ("real axis celtic p128", lambda: make_view("-0.5", "0.0", "3.5", 64, 48, precision=128, depth=500, fractal=GENERALIZED_CELTIC), 64),
+    ("real axis hybrid p320", lambda: make_view("-0.5", "0.0", "3.5", 64, 48, precision=320, depth=500, fractal=VARIANT), 64),
 ]
 
 
@@ -82,6 +87,22 @@ def test_pixels_match_reference(emu, ref_lib, name, mk, count, spec):
         ix, line = (k * 37 + 5) % W, (k * 53 + (H // 2 if k % 4 == 0 else 3)) % H
         x, y = coords(view, ix, line)
         assert emu_pixel(emu, view, x, y, spec) == ref_pixel(ref_lib, view, x, y), (name, ix, line)
+
+
+@pytest.mark.parametrize("fractal", [MANDELBROT, BURNING_SHIP, GENERALIZED_CELTIC, VARIANT])
+@pytest.mark.parametrize("prec", [64, 96, 320])
+def test_real_axis_shortcut_matches_reference(emu, ref_lib, fractal, prec):
+    """y exactly 0: pixel_step's real-orbit shortcut (escape_step.cuh: wre = RN(wre2 + c_re),
+    wre2 = RN(wre^2), wim stays 0) against the reference's nine-call loop body on points of the
+    real axis -- interior, the chaotic part of the antenna, the tip at -2, and outside."""
+    view = make_view("-0.75", "0.0", "2.5", 64, 48, precision=prec, depth=3000, fractal=fractal)
+    zero = Mpfr(prec, 0)
+    for xs in ("-2", "-1.9999", "-1.75", "-1.5436890126920763", "-1.25", "-1", "-0.75", "-0.1", "0", "0.2",
+               "0.25", "0.2500001", "0.3", "1", "2", "-2.0000001"):
+        x = Mpfr(prec, xs)
+        want = ref_pixel(ref_lib, view, x, zero)
+        for spec in (0, 1, 3):
+            assert emu_pixel(emu, view, x, zero, spec) == want, (fractal, prec, xs, spec)
 
 
 # ---- GMP mpf mode: mpf_sf.cuh gmp_pixel_* vs the reference's frac_*_gmp -------------

@@ -18,6 +18,10 @@ def case(name, scale=1.0):
     w, h = int(960 * scale), int(540 * scale)
     if name == "ld":
         return config2(2 * w, 2 * h, 10000)
+    if name.startswith("int"):
+        # every pixel inside the main cardioid: `lanes` pixels that all run to depth (per-warp pace at a given occupancy)
+        lanes = int(name[3:] or 113664)
+        return make_view("-0.1", "0.2", "0.1", 1024, lanes // 1024, mode="ld", depth=10000)
     if name.startswith("mpfr"):
         p = int(name[4:])
         if p == 320:
@@ -39,9 +43,10 @@ ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--chunk", type=int, default=0)
 ap.add_argument("--bps", type=int, default=0)
 ap.add_argument("--cycle", type=int, default=0, help="1: exact periodicity check on")
+ap.add_argument("--stride", type=int, default=1, help="render bands 0, stride, 2*stride, ... only (one rank's share of a strong-scaled render)")
 a = ap.parse_args()
 v = case(a.case, a.scale)
-plan = mdz_b200.Plan(v, 0)
+plan = mdz_b200.Plan(v, 0, 0, a.stride)
 plan.tune(a.chunk, a.bps)
 plan.set_cycle_detection(bool(a.cycle))
 for i in range(a.reps):
@@ -51,4 +56,5 @@ for i in range(a.reps):
     dt = time.perf_counter() - t0
     raw = plan.fetch()
     it = int(np.where(raw > 0, raw, v.depth).astype(np.int64).sum())
-    print("%s rep %d: %.2f ms, %d iterations, %.3f G it/s, kernel %s" % (a.case, i, dt * 1e3, it, it / dt / 1e9, plan.kernel_info()))
+    import zlib
+    print("%s rep %d: %.2f ms, %d iterations, %.3f G it/s, crc %08x, kernel %s" % (a.case, i, dt * 1e3, it, it / dt / 1e9, zlib.crc32(raw.tobytes()), plan.kernel_info()))
