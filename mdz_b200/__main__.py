@@ -17,14 +17,9 @@ from .png import write_png
 
 def load_map(path):
     """.map palette: up to 256 lines " R G B" (reference src/palette.c:142-168)."""
-    pal = []
-    for ln in open(path):
-        parts = ln.split()
-        if len(pal) >= 256 or len(parts) != 3:
-            break
-        r, g, b = (int(x) for x in parts)
-        pal.append(r | (g << 8) | (b << 16))
-    return pal
+    from .palette import Palette
+    pal = Palette.load(path)
+    return pal.colours if pal is not None else None
 
 
 def main(argv=None):
