@@ -215,17 +215,18 @@ escape_mpfr_kernel(const EscapeParams p)
                 cim.m[0] = cim_m[0]; cim.m[1] = cim_m[kScratchStride]; cim.e = st.cim_e; cim.s = st.cim_s;
                 cre.m[0] = cre_m[0]; cre.m[1] = cre_m[kScratchStride]; cre.e = st.cre_e; cre.s = st.cre_s;
                 PixelState<2> nx;
+                const Ld64Masks mk = ld64_masks(abs_im, abs_re);
                 for (int k = 0; k < p.chunk; ++k) {
                     // two iterations per trip, st -> nx -> st, so that no state is copied back
                     bool rare = false;
-                    bool esc = ld64_step(st, nx, cre, cim, scr, p.rc, abs_im, abs_re, rare);
+                    bool esc = ld64_step(st, nx, cre, cim, scr, p.rc, mk, rare);
                     bool cyc_ev = CYC && ((nx.wre.m[0] == cyc.f0 && nx.wim.m[0] == cyc.f1) || nx.iter == cyc.next);
                     bool ev = active && (rare || esc || nx.iter >= p.depth || cyc_ev);
                     warp_steps += 1;
                     if (!__any_sync(0xffffffffu, ev)) {
                         if (++k >= p.chunk) { st = nx; break; }
                         rare = false;
-                        esc = ld64_step(nx, st, cre, cim, scr, p.rc, abs_im, abs_re, rare);
+                        esc = ld64_step(nx, st, cre, cim, scr, p.rc, mk, rare);
                         cyc_ev = CYC && ((st.wre.m[0] == cyc.f0 && st.wim.m[0] == cyc.f1) || st.iter == cyc.next);
                         ev = active && (rare || esc || st.iter >= p.depth || cyc_ev);
                         warp_steps += 1;

@@ -69,75 +69,140 @@ MDZ_HD void addsub128(uint32_t (&x)[4], uint32_t a1, uint32_t a2, uint32_t a3, c
 }
 #endif
 
+// 1 when bit 31 of x is clear, as a register value: written out because the compiler turns the
+// plain expression, applied to the top half of a 64-bit product, into a 64-bit compare + select
+// and then needs two more instructions to subtract the resulting predicate from the exponent
+#if defined(MDZ_HOST_EMU)
+inline uint32_t top_clear(uint32_t x) { return (x >> 31) ^ 1u; }
+#else
+MDZ_HD uint32_t top_clear(uint32_t x)
+{
+    uint32_t r;
+    asm("{\n\t.reg .u32 t;\n\tshr.u32 t, %1, 31;\n\txor.b32 %0, t, 1;\n\t}" : "=r"(r) : "r"(x));
+    return r;
+}
+#endif
+
+// The fast operations report what they cannot do through three accumulators instead of a
+// predicate per operation (thirteen compares per iteration otherwise):
+//   topand  AND of the top words of every result: its bit 31 is clear as soon as one result lost
+//           its leading bit (zero factor, 31 or more cancelled bits, rounding carried out)
+//   negor   OR of the top words of the differences' 128-bit frames: bit 31 set means one came out
+//           negative (operands with equal exponents and top words, ordered by those alone)
+//   rare    the remaining tests (exponent gap beyond the frame, product exponent below E_MIN)
+struct Ld64Flags {
+    uint32_t topand, negor;
+    bool rare;
+};
+MDZ_HD void ld64_flags_init(Ld64Flags& f, bool rare) { f.topand = 0xffffffffu; f.negor = 0u; f.rare = rare; }
+MDZ_HD bool ld64_flags_rare(const Ld64Flags& f) { return f.rare || (int32_t)(~f.topand | f.negor) < 0; }
+
 // r = RN(a * b): the sign is left to the caller.  A product just below a power of two
 // (top bit at 126, all ones after the one-bit shift) can round up past 2^64; the top-bit
 // test catches that and a zero operand.
-MDZ_HD void mul64_spec(const Num<2>& a, const Num<2>& b, Num<2>& r, bool& rare)
+MDZ_HD void mul64_core(const Num<2>& a, const Num<2>& b, Num<2>& r, Ld64Flags& f)
 {
     const uint64_t p00 = (uint64_t)a.m[0] * b.m[0];
     const uint64_t t   = (uint64_t)a.m[1] * b.m[0] + (uint32_t)(p00 >> 32);
     const uint64_t u   = (uint64_t)a.m[0] * b.m[1] + (uint32_t)t;
     const uint64_t hi  = (uint64_t)a.m[1] * b.m[1] + (uint32_t)(t >> 32) + (uint32_t)(u >> 32);
     const uint32_t p0 = (uint32_t)p00, p1 = (uint32_t)u, p2 = (uint32_t)hi, p3 = (uint32_t)(hi >> 32);
-    const uint32_t sh = (p3 >> 31) ^ 1u;             // top bit at 127 or 126
+    const uint32_t sh = top_clear(p3);               // top bit at 127 or 126
     const uint32_t x3 = fsl(p2, p3, sh), x2 = fsl(p1, p2, sh), x1 = fsl(p0, p1, sh), x0 = p0 << sh;
     round_rne64(r.m[0], r.m[1], x2, x3, x0, x1);
     r.e = a.e + b.e - (int32_t)sh;
-    rare = rare || (int32_t)r.m[1] >= 0 || r.e < E_MIN;
+    f.topand &= r.m[1];
+    f.rare = f.rare || r.e < E_MIN;
+}
+MDZ_HD void mul64_spec(const Num<2>& a, const Num<2>& b, Num<2>& r, bool& rare)
+{
+    Ld64Flags f; ld64_flags_init(f, rare);
+    mul64_core(a, b, r, f);
+    rare = ld64_flags_rare(f);
 }
 
-// r = RN(a + b) with the signs as given
-MDZ_HD void add64_spec(const Num<2>& a, const Num<2>& b, Num<2>& r, bool& rare)
+// r = RN(a + b) with the signs as given.  The operands are ordered by (exponent, top word) alone --
+// one 64-bit compare.  When those are equal an addition does not care about the order; a
+// difference then cancels 32 bits or more, which is outside this function's domain anyway: it
+// comes out with a zero top word (caught by topand) or negative (caught by negor).
+MDZ_HD void add64_core(const Num<2>& a, const Num<2>& b, Num<2>& r, Ld64Flags& f)
 {
     const int32_t d = a.e - b.e;
-    const uint64_t am = ((uint64_t)a.m[1] << 32) | a.m[0], bm = ((uint64_t)b.m[1] << 32) | b.m[0];
-    const bool swap = d < 0 || (d == 0 && am < bm);             // |A| >= |B| afterwards
+    const int64_t ka = (int64_t)(((uint64_t)(uint32_t)a.e << 32) | a.m[1]);
+    const int64_t kb = (int64_t)(((uint64_t)(uint32_t)b.e << 32) | b.m[1]);
+    const bool swap = ka < kb;                                  // |A| >= |B| afterwards, up to the low words
     const uint32_t A0 = swap ? b.m[0] : a.m[0], A1 = swap ? b.m[1] : a.m[1];
-    const uint64_t Bm = swap ? am : bm;
+    const uint32_t B0 = swap ? a.m[0] : b.m[0], B1 = swap ? a.m[1] : b.m[1];
+    const uint64_t Bm = ((uint64_t)B1 << 32) | B0;
     const int32_t Ae = swap ? b.e : a.e;
     const uint32_t ad = (uint32_t)(d < 0 ? -d : d);
-    rare = rare || ad > 62u;
+    f.rare = f.rare || ad > 62u;
     // 128-bit frame with one bit of headroom: A >> 1, B >> (ad + 1); nothing of B
-    // leaves the frame while ad <= 62, so the sum is exact
+    // leaves the frame while ad <= 62, so the sum is exact.  (Measured alternative, rejected:
+    // letting a B below a quarter of A's last place -- gap >= 66, or an exact zero -- enter as one
+    // sticky bit keeps the nearly real orbits next to y = 0 inside this step, but costs three
+    // instructions per addition: 4 % on every other pixel.)
     const uint64_t BH = shr64c(Bm, ad + 1u), BL = shl64c(Bm, 63u - ad);
     const uint32_t bw[4] = { (uint32_t)BL, (uint32_t)(BL >> 32), (uint32_t)BH, (uint32_t)(BH >> 32) };
     const uint32_t mask = (a.s != b.s) ? 0xffffffffu : 0u;
     uint32_t x[4];
     addsub128(x, A0 << 31, fsr(A0, A1, 1), A1 >> 1, bw, mask);
+    f.negor |= x[3] & mask;                                     // bit 127 is the sums' carry; a difference sets it only when negative
     // normalise.  31 or more cancelled bits (top word zero, about one addition in a million
     // on orbit data) are left to the general code: lz is then 32, the funnel shifts move
-    // nothing, and the zero top word fails the top-bit test below
+    // nothing, and the zero top word fails the top-bit test
     const int32_t e = Ae + 1;
     const uint32_t lz = (uint32_t)clz32(x[3]);
     const uint32_t h1 = fsl(x[2], x[3], lz), h0 = fsl(x[1], x[2], lz), l1 = fsl(x[0], x[1], lz), l0 = x[0] << lz;
     round_rne64(r.m[0], r.m[1], h0, h1, l0, l1);
     // top bit clear: >= 31 bits cancelled / exact zero, or the increment carried out
-    rare = rare || (int32_t)r.m[1] >= 0;
+    f.topand &= r.m[1];
     r.e = e - (int32_t)lz;
     r.s = swap ? b.s : a.s;
+}
+MDZ_HD void add64_spec(const Num<2>& a, const Num<2>& b, Num<2>& r, bool& rare)
+{
+    Ld64Flags f; ld64_flags_init(f, rare);
+    add64_core(a, b, r, f);
+    rare = ld64_flags_rare(f);
 }
 
 // One iteration from `in` to `out` (distinct objects: the kernel's hot loop ping-pongs
 // between two register sets instead of copying the state back), c passed by value so that it
 // can live in registers.  `rare` comes back true when the step declined; `out` is then garbage.
+// The fractal type enters as three words that stay in registers across a chunk (ld64_masks):
+// the product's sign is kept (1) or dropped (0: burning ship); the difference loses its sign always
+// (re_always = 1: generalized celtic) or on odd iterations (re_odd = 1: the hybrid).
+struct Ld64Masks { uint32_t im_keep, re_always, re_odd; };
+MDZ_HD Ld64Masks ld64_masks(bool abs_im, int abs_re)
+{
+    Ld64Masks m;
+    m.im_keep = abs_im ? 0u : 1u;
+    m.re_always = abs_re == 1 ? 1u : 0u;
+    m.re_odd = abs_re == 2 ? 1u : 0u;
+    return m;
+}
+
 MDZ_HD bool ld64_step(const PixelState<2>& in, PixelState<2>& out, const Num<2>& cre, const Num<2>& cim,
-                      uint32_t* scr, const RoundCfg& rc, bool abs_im, int abs_re, bool& rare)
+                      uint32_t* scr, const RoundCfg& rc, const Ld64Masks& mk, bool& rare)
 {
     out.iter = in.iter + 1;
     out.cre_e = in.cre_e; out.cim_e = in.cim_e; out.cre_s = in.cre_s; out.cim_s = in.cim_s;
+    Ld64Flags f; ld64_flags_init(f, rare);
     Num<2> t, u, nw;
     // wim = 2*wre*wim + c_im
-    mul64_spec(in.wre, in.wim, t, rare);
+    mul64_core(in.wre, in.wim, t, f);
     t.e += 1;
-    t.s = abs_im ? 0u : (in.wre.s ^ in.wim.s);
+    t.s = (in.wre.s ^ in.wim.s) & mk.im_keep;
     // wre = wre2 - wim2 + c_re
     nw = in.wim2; nw.s = 1u;
-    add64_spec(in.wre2, nw, u, rare);
-    if (abs_re == 1 || (abs_re == 2 && (out.iter & 1))) u.s = 0;
-    add64_spec(t, cim, out.wim, rare);
-    add64_spec(u, cre, out.wre, rare);
-    mul64_spec(out.wim, out.wim, out.wim2, rare);
-    mul64_spec(out.wre, out.wre, out.wre2, rare);
+    add64_core(in.wre2, nw, u, f);
+    u.s &= ~(mk.re_always | (mk.re_odd & (uint32_t)out.iter));
+    add64_core(t, cim, out.wim, f);
+    add64_core(u, cre, out.wre, f);
+    mul64_core(out.wim, out.wim, out.wim2, f);
+    mul64_core(out.wre, out.wre, out.wre2, f);
+    rare = ld64_flags_rare(f);
     out.wim2.s = 0; out.wre2.s = 0;
     const int32_t emax = out.wim2.e > out.wre2.e ? out.wim2.e : out.wre2.e;
     bool esc = emax >= 4;
@@ -166,7 +231,7 @@ MDZ_HD bool pixel_step_spec<2>(PixelState<2>& st, const uint32_t* cre_m, const u
     cim.m[0] = cim_m[0]; cim.m[1] = cim_m[kScratchStride]; cim.e = st.cim_e; cim.s = st.cim_s;
     cre.m[0] = cre_m[0]; cre.m[1] = cre_m[kScratchStride]; cre.e = st.cre_e; cre.s = st.cre_s;
     PixelState<2> out;
-    const bool esc = ld64_step(st, out, cre, cim, scr, rc, abs_im, abs_re, rare);
+    const bool esc = ld64_step(st, out, cre, cim, scr, rc, ld64_masks(abs_im, abs_re), rare);
     st = out;
     rare_out |= rare ? 1u : 0u;
     return esc;
