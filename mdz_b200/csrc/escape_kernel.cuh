@@ -215,7 +215,7 @@ escape_mpfr_kernel(const EscapeParams p)
                 cim.m[0] = cim_m[0]; cim.m[1] = cim_m[kScratchStride]; cim.e = st.cim_e; cim.s = st.cim_s;
                 cre.m[0] = cre_m[0]; cre.m[1] = cre_m[kScratchStride]; cre.e = st.cre_e; cre.s = st.cre_s;
                 PixelState<2> nx;
-                const Ld64Masks mk = ld64_masks(abs_im, abs_re);
+                const Ld64Masks mk = p.ld_masks;
                 for (int k = 0; k < p.chunk; ++k) {
                     // two iterations per trip, st -> nx -> st, so that no state is copied back
                     bool rare = false;

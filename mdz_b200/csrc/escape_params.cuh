@@ -3,6 +3,7 @@
 #pragma once
 #include <stdint.h>
 #include "mpfr_sf.cuh"
+#include "escape_step.cuh"
 #include "colour.cuh"
 
 namespace mdz {
@@ -41,6 +42,7 @@ struct EscapeParams {
     int cycle;              // 1: exact periodicity check (escape_kernel.cuh); MPFR / long double kernels only
     uint32_t* cycle_scratch;    // [2N+3][grid threads] saved states, when cycle != 0
     ColourParams colour;    // fused epilogue: colour a band as soon as it completes (enabled = 0: raw only)
+    Ld64Masks ld_masks;     // ld64_masks(fractal), filled in by the host so that the hot loop reads them as constants
 };
 
 constexpr int kBlock = 128;

@@ -16,6 +16,9 @@ namespace mdz {
 enum { FRACTAL_MANDELBROT = 0, FRACTAL_BURNING_SHIP = 1, FRACTAL_GENERALIZED_CELTIC = 2, FRACTAL_VARIANT = 3 };
 enum { FAMILY_MANDEL = 0, FAMILY_JULIA = 1 };
 
+// how the fractal type enters the long double mode's fast iteration (ld64_step.cuh: ld64_masks)
+struct Ld64Masks { uint32_t im_keep, re_and, re_xor; };
+
 template <int N>
 struct PixelState {
     Num<N> wre, wim, wre2, wim2;

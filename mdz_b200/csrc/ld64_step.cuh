@@ -102,6 +102,9 @@ MDZ_HD bool ld64_flags_rare(const Ld64Flags& f) { return f.rare || (int32_t)(~f.
 // test catches that and a zero operand.
 MDZ_HD void mul64_core(const Num<2>& a, const Num<2>& b, Num<2>& r, Ld64Flags& f)
 {
+    // (Measured alternative, rejected: limb_ops.cuh mul_full<2> -- aligned accumulator pairs, no
+    // zero-extension moves -- trades six IMAD.MOV on the idle FMA pipe for one more add on the ALU pipe,
+    // which is the one that binds: 13.3 against 12.65 ms per generation.)
     const uint64_t p00 = (uint64_t)a.m[0] * b.m[0];
     const uint64_t t   = (uint64_t)a.m[1] * b.m[0] + (uint32_t)(p00 >> 32);
     const uint64_t u   = (uint64_t)a.m[0] * b.m[1] + (uint32_t)t;
@@ -170,16 +173,17 @@ MDZ_HD void add64_spec(const Num<2>& a, const Num<2>& b, Num<2>& r, bool& rare)
 // One iteration from `in` to `out` (distinct objects: the kernel's hot loop ping-pongs
 // between two register sets instead of copying the state back), c passed by value so that it
 // can live in registers.  `rare` comes back true when the step declined; `out` is then garbage.
-// The fractal type enters as three words that stay in registers across a chunk (ld64_masks):
-// the product's sign is kept (1) or dropped (0: burning ship); the difference loses its sign always
-// (re_always = 1: generalized celtic) or on odd iterations (re_odd = 1: the hybrid).
-struct Ld64Masks { uint32_t im_keep, re_always, re_odd; };
+// The fractal type enters as three words (EscapeParams::ld_masks, read straight from the constant
+// bank: computed inside the kernel the compiler re-derives them from the type in every iteration, ten
+// instructions): the product's sign is kept (im_keep = 1) or dropped (0: burning ship); the
+// difference keeps its sign when ((iteration & re_and) ^ re_xor) is 1 -- always (0, 1), never (0, 0:
+// generalized celtic), on even iterations (1, 1: the hybrid).
 MDZ_HD Ld64Masks ld64_masks(bool abs_im, int abs_re)
 {
     Ld64Masks m;
     m.im_keep = abs_im ? 0u : 1u;
-    m.re_always = abs_re == 1 ? 1u : 0u;
-    m.re_odd = abs_re == 2 ? 1u : 0u;
+    m.re_and = abs_re == 2 ? 1u : 0u;
+    m.re_xor = abs_re == 1 ? 0u : 1u;
     return m;
 }
 
@@ -197,7 +201,7 @@ MDZ_HD bool ld64_step(const PixelState<2>& in, PixelState<2>& out, const Num<2>&
     // wre = wre2 - wim2 + c_re
     nw = in.wim2; nw.s = 1u;
     add64_core(in.wre2, nw, u, f);
-    u.s &= ~(mk.re_always | (mk.re_odd & (uint32_t)out.iter));
+    u.s &= ((uint32_t)out.iter & mk.re_and) ^ mk.re_xor;
     add64_core(t, cim, out.wim, f);
     add64_core(u, cre, out.wre, f);
     mul64_core(out.wim, out.wim, out.wim2, f);

@@ -700,6 +700,9 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         p.spec = pl->spec;
         if (p.spec == 1) { static const int forced = [] { const char* e = getenv("MDZCUDA_SPEC_LEVEL"); return e && *e ? atoi(e) : 1; }(); p.spec = forced; }   // A/B: 2 / 3 pin level 1 / 2
         p.colour = pl->colour;
+        p.ld_masks.im_keep = p.fractal == FRACTAL_BURNING_SHIP ? 0u : 1u;           // ld64_step.cuh: ld64_masks
+        p.ld_masks.re_and = p.fractal == FRACTAL_VARIANT ? 1u : 0u;
+        p.ld_masks.re_xor = p.fractal == FRACTAL_GENERALIZED_CELTIC ? 0u : 1u;
         const int cyc = (pl->cycle && !pl->gmp) ? 1 : 0;
         kernel_fn fn = pl->gmp ? gmp_kernel_for_limbs(pl->n32 / 2) : kernel_for_limbs(pl->n32, cyc);
         if (!fn) { set_err("no kernel for %d limbs", pl->n32); return 0; }
