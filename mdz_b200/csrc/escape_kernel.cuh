@@ -124,6 +124,63 @@ __device__ __noinline__ bool cycle_match(const EscapeParams& p, const PixelState
     return (diff | dt) == 0;
 }
 
+// One chunk of the long double mode's event-driven loop (ld64_step.cuh).  The iteration is one
+// branch-free block that every lane runs, finished lanes included (their results are ignored); the
+// warp leaves that block only when some lane has an event -- escaped, reached depth, or met a case
+// the fast step declines -- so an interior pixel's ten thousand iterations cost one vote and one
+// branch each on top of the arithmetic.  WIDE: level 2, the additions of add64_core<true>.
+template <bool CYC, bool WIDE>
+__device__ __forceinline__ void ld64_event_chunk(const EscapeParams& p, PixelState<2>& st, uint32_t* cre_m, uint32_t* cim_m,
+                                                 uint32_t* scr, bool& active, const unsigned& pix, int& finished_band,
+                                                 CycleState& cyc, uint32_t& rare_seen, int& warp_steps, int& warp_fell,
+                                                 const unsigned lane, const bool abs_im, const int abs_re)
+{
+    Num<2> cre, cim;                         // c stays in registers across the chunk
+    cim.m[0] = cim_m[0]; cim.m[1] = cim_m[kScratchStride]; cim.e = st.cim_e; cim.s = st.cim_s;
+    cre.m[0] = cre_m[0]; cre.m[1] = cre_m[kScratchStride]; cre.e = st.cre_e; cre.s = st.cre_s;
+    PixelState<2> nx;
+    const Ld64Masks mk = p.ld_masks;
+    for (int k = 0; k < p.chunk; ++k) {
+        // two iterations per trip, st -> nx -> st, so that no state is copied back
+        bool rare = false;
+        bool esc = ld64_step<WIDE>(st, nx, cre, cim, scr, p.rc, mk, rare);
+        bool cyc_ev = CYC && ((nx.wre.m[0] == cyc.f0 && nx.wim.m[0] == cyc.f1) || nx.iter == cyc.next);
+        bool ev = active && (rare || esc || nx.iter >= p.depth || cyc_ev);
+        warp_steps += 1;
+        if (!__any_sync(0xffffffffu, ev)) {
+            if (++k >= p.chunk) { st = nx; break; }
+            rare = false;
+            esc = ld64_step<WIDE>(nx, st, cre, cim, scr, p.rc, mk, rare);
+            cyc_ev = CYC && ((st.wre.m[0] == cyc.f0 && st.wim.m[0] == cyc.f1) || st.iter == cyc.next);
+            ev = active && (rare || esc || st.iter >= p.depth || cyc_ev);
+            warp_steps += 1;
+            if (!__any_sync(0xffffffffu, ev)) continue;
+            // event in the second half: present it to the handler as (old = st, new = nx)
+            const PixelState<2> tmp = st; st = nx; nx = tmp;
+        }
+        warp_fell += __any_sync(0xffffffffu, active && rare) ? 1 : 0;
+        if (active) {
+            if (rare) { rare_seen += 1; esc = pixel_step<2>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re); }
+            else st = nx;
+            bool periodic = false;
+            if (CYC && !esc) {
+                if (st.wre.m[0] == cyc.f0 && st.wim.m[0] == cyc.f1) periodic = cycle_match<2>(p, st);
+                if (!periodic && st.iter >= cyc.next) cycle_save<2>(p, st, cyc);
+            }
+            if (esc || periodic || st.iter >= p.depth) {
+                p.raw[pix] = esc ? st.iter : 0;
+                __threadfence();
+                active = false;
+                const unsigned band = (pix / (unsigned)p.width) / (unsigned)p.aa;
+                const unsigned done = atomicAdd(&p.band_count[band], 1u) + 1u;
+                if (done == (unsigned)p.width * (unsigned)p.aa) finished_band = (int)band;
+            }
+        }
+        if (publish_bands(p, finished_band, lane)) finished_band = -1;
+        if (!__any_sync(0xffffffffu, active)) break;
+    }
+}
+
 // CYC: compiled with the exact periodicity check.  A separate instantiation, because the
 // extra state and cold paths cost the plain kernels 7-15 % when merely present.
 template <int N, bool CYC>
@@ -205,56 +262,13 @@ escape_mpfr_kernel(const EscapeParams p)
         bool event_loop = false;
         if constexpr (N == 2) event_loop = spec_level != 0 && p.rc.ulp == 1u;   // the 64-bit step needs p = 64 exactly
         if (event_loop) {
-            // Long double mode (ld64_step.cuh).  The iteration is one branch-free block that
-            // every lane runs, finished lanes included (their results are ignored); the warp
-            // leaves that block only when some lane has an event -- escaped, reached depth,
-            // or met a case the fast step declines -- so an interior pixel's ten thousand
-            // iterations cost one vote and one branch each on top of the arithmetic.
             if constexpr (N == 2) {
-                Num<2> cre, cim;                         // c stays in registers across the chunk
-                cim.m[0] = cim_m[0]; cim.m[1] = cim_m[kScratchStride]; cim.e = st.cim_e; cim.s = st.cim_s;
-                cre.m[0] = cre_m[0]; cre.m[1] = cre_m[kScratchStride]; cre.e = st.cre_e; cre.s = st.cre_s;
-                PixelState<2> nx;
-                const Ld64Masks mk = p.ld_masks;
-                for (int k = 0; k < p.chunk; ++k) {
-                    // two iterations per trip, st -> nx -> st, so that no state is copied back
-                    bool rare = false;
-                    bool esc = ld64_step(st, nx, cre, cim, scr, p.rc, mk, rare);
-                    bool cyc_ev = CYC && ((nx.wre.m[0] == cyc.f0 && nx.wim.m[0] == cyc.f1) || nx.iter == cyc.next);
-                    bool ev = active && (rare || esc || nx.iter >= p.depth || cyc_ev);
-                    warp_steps += 1;
-                    if (!__any_sync(0xffffffffu, ev)) {
-                        if (++k >= p.chunk) { st = nx; break; }
-                        rare = false;
-                        esc = ld64_step(nx, st, cre, cim, scr, p.rc, mk, rare);
-                        cyc_ev = CYC && ((st.wre.m[0] == cyc.f0 && st.wim.m[0] == cyc.f1) || st.iter == cyc.next);
-                        ev = active && (rare || esc || st.iter >= p.depth || cyc_ev);
-                        warp_steps += 1;
-                        if (!__any_sync(0xffffffffu, ev)) continue;
-                        // event in the second half: present it to the handler as (old = st, new = nx)
-                        const PixelState<2> tmp = st; st = nx; nx = tmp;
-                    }
-                    warp_fell += __any_sync(0xffffffffu, active && rare) ? 1 : 0;
-                    if (active) {
-                        if (rare) { rare_seen += 1; esc = pixel_step<2>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re); }
-                        else st = nx;
-                        bool periodic = false;
-                        if (CYC && !esc) {
-                            if (st.wre.m[0] == cyc.f0 && st.wim.m[0] == cyc.f1) periodic = cycle_match<2>(p, st);
-                            if (!periodic && st.iter >= cyc.next) cycle_save<2>(p, st, cyc);
-                        }
-                        if (esc || periodic || st.iter >= p.depth) {
-                            p.raw[pix] = esc ? st.iter : 0;
-                            __threadfence();
-                            active = false;
-                            const unsigned band = (pix / (unsigned)p.width) / (unsigned)p.aa;
-                            const unsigned done = atomicAdd(&p.band_count[band], 1u) + 1u;
-                            if (done == (unsigned)p.width * (unsigned)p.aa) finished_band = (int)band;
-                        }
-                    }
-                    if (publish_bands(p, finished_band, lane)) finished_band = -1;
-                    if (!__any_sync(0xffffffffu, active)) break;
-                }
+                if (spec_level == 2)
+                    ld64_event_chunk<CYC, true>(p, st, cre_m, cim_m, scr, active, pix, finished_band, cyc,
+                                                rare_seen, warp_steps, warp_fell, lane, abs_im, abs_re);
+                else
+                    ld64_event_chunk<CYC, false>(p, st, cre_m, cim_m, scr, active, pix, finished_band, cyc,
+                                                 rare_seen, warp_steps, warp_fell, lane, abs_im, abs_re);
             }
         } else
         for (int k = 0; k < p.chunk; ++k) {
@@ -302,7 +316,7 @@ escape_mpfr_kernel(const EscapeParams p)
                 if (warp_fell * 4 > warp_steps) {
                     spec_backoff = spec_backoff < 4096 ? spec_backoff * 2 : 4096;
                     spec_pause = spec_backoff;
-                    spec_level = (spec_level == 1 && N > 2) ? 2 : 0;
+                    spec_level = spec_level == 1 ? 2 : 0;
                 } else if (spec_level == 2) {
                     if (--spec_pause <= 0) spec_level = 1;          // see whether the narrow one will do again
                 } else if (warp_fell == 0) spec_backoff = 8;

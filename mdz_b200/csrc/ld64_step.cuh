@@ -128,25 +128,41 @@ MDZ_HD void mul64_spec(const Num<2>& a, const Num<2>& b, Num<2>& r, bool& rare)
 // one 64-bit compare.  When those are equal an addition does not care about the order; a
 // difference then cancels 32 bits or more, which is outside this function's domain anyway: it
 // comes out with a zero top word (caught by topand) or negative (caught by negor).
+//
+// WIDE is the kernel's level 2 in long double mode, for warps that hold pixels on which the plain
+// version declines at every iteration (escape_kernel.cuh "adapt"), at ~10 instructions more per
+// addition:
+//  * a second operand below a quarter of the first one's last place -- exponent gap >= 66, or an
+//    exact zero, e.g. c_re on the column x = 0 or wim^2 next to the real axis -- only has to be there,
+//    and on which side: it enters as one sticky bit at the bottom of the frame (the clamped shifts
+//    have already made it 0).  A - B with A a power of two is the one case a quarter ulp can decide;
+//    the difference then normalises to all ones, the increment carries out, and the top-bit test
+//    declines.  Gaps of 64 and 65 stay with the general code;
+//  * 32 to 62 cancelled bits are normalised by a word move first (orbits that converge to a fixed
+//    point on a diagonal, |wre| = |wim|, cancel wre^2 - wim^2 almost completely for ever).
+// On BASELINE configs[1] ~1 700 interior pixels of the first kind and 13 of the second used to run
+// the general step 10 000 times each, alone in their warps: the end of every render waited for them.
+template <bool WIDE = false>
 MDZ_HD void add64_core(const Num<2>& a, const Num<2>& b, Num<2>& r, Ld64Flags& f)
 {
     const int32_t d = a.e - b.e;
     const int64_t ka = (int64_t)(((uint64_t)(uint32_t)a.e << 32) | a.m[1]);
     const int64_t kb = (int64_t)(((uint64_t)(uint32_t)b.e << 32) | b.m[1]);
-    const bool swap = ka < kb;                                  // |A| >= |B| afterwards, up to the low words
+    // |A| >= |B| afterwards, up to the low words; level 2 normalises deep cancellation itself, so
+    // there the low words have their say as well
+    const bool swap = WIDE ? (d < 0 || (d == 0 && (((uint64_t)a.m[1] << 32) | a.m[0]) < (((uint64_t)b.m[1] << 32) | b.m[0])))
+                           : ka < kb;
     const uint32_t A0 = swap ? b.m[0] : a.m[0], A1 = swap ? b.m[1] : a.m[1];
     const uint32_t B0 = swap ? a.m[0] : b.m[0], B1 = swap ? a.m[1] : b.m[1];
     const uint64_t Bm = ((uint64_t)B1 << 32) | B0;
     const int32_t Ae = swap ? b.e : a.e;
     const uint32_t ad = (uint32_t)(d < 0 ? -d : d);
-    f.rare = f.rare || ad > 62u;
+    if (WIDE) f.rare = f.rare || (ad - 64u) < 2u; else f.rare = f.rare || ad > 62u;
     // 128-bit frame with one bit of headroom: A >> 1, B >> (ad + 1); nothing of B
-    // leaves the frame while ad <= 62, so the sum is exact.  (Measured alternative, rejected:
-    // letting a B below a quarter of A's last place -- gap >= 66, or an exact zero -- enter as one
-    // sticky bit keeps the nearly real orbits next to y = 0 inside this step, but costs three
-    // instructions per addition: 4 % on every other pixel.)
+    // leaves the frame while ad <= 63, so the sum is exact
     const uint64_t BH = shr64c(Bm, ad + 1u), BL = shl64c(Bm, 63u - ad);
-    const uint32_t bw[4] = { (uint32_t)BL, (uint32_t)(BL >> 32), (uint32_t)BH, (uint32_t)(BH >> 32) };
+    const uint32_t sticky = (WIDE && ad > 65u) ? 1u : 0u;
+    const uint32_t bw[4] = { (uint32_t)BL | sticky, (uint32_t)(BL >> 32), (uint32_t)BH, (uint32_t)(BH >> 32) };
     const uint32_t mask = (a.s != b.s) ? 0xffffffffu : 0u;
     uint32_t x[4];
     addsub128(x, A0 << 31, fsr(A0, A1, 1), A1 >> 1, bw, mask);
@@ -154,7 +170,12 @@ MDZ_HD void add64_core(const Num<2>& a, const Num<2>& b, Num<2>& r, Ld64Flags& f
     // normalise.  31 or more cancelled bits (top word zero, about one addition in a million
     // on orbit data) are left to the general code: lz is then 32, the funnel shifts move
     // nothing, and the zero top word fails the top-bit test
-    const int32_t e = Ae + 1;
+    int32_t e = Ae + 1;
+    if (WIDE) {
+        const bool z = x[3] == 0u;                              // 32 bits or more cancelled: one word up
+        x[3] = z ? x[2] : x[3]; x[2] = z ? x[1] : x[2]; x[1] = z ? x[0] : x[1]; x[0] = z ? 0u : x[0];
+        e -= z ? 32 : 0;
+    }
     const uint32_t lz = (uint32_t)clz32(x[3]);
     const uint32_t h1 = fsl(x[2], x[3], lz), h0 = fsl(x[1], x[2], lz), l1 = fsl(x[0], x[1], lz), l0 = x[0] << lz;
     round_rne64(r.m[0], r.m[1], h0, h1, l0, l1);
@@ -163,10 +184,11 @@ MDZ_HD void add64_core(const Num<2>& a, const Num<2>& b, Num<2>& r, Ld64Flags& f
     r.e = e - (int32_t)lz;
     r.s = swap ? b.s : a.s;
 }
+template <bool WIDE = false>
 MDZ_HD void add64_spec(const Num<2>& a, const Num<2>& b, Num<2>& r, bool& rare)
 {
     Ld64Flags f; ld64_flags_init(f, rare);
-    add64_core(a, b, r, f);
+    add64_core<WIDE>(a, b, r, f);
     rare = ld64_flags_rare(f);
 }
 
@@ -187,6 +209,7 @@ MDZ_HD Ld64Masks ld64_masks(bool abs_im, int abs_re)
     return m;
 }
 
+template <bool WIDE = false>
 MDZ_HD bool ld64_step(const PixelState<2>& in, PixelState<2>& out, const Num<2>& cre, const Num<2>& cim,
                       uint32_t* scr, const RoundCfg& rc, const Ld64Masks& mk, bool& rare)
 {
@@ -200,10 +223,10 @@ MDZ_HD bool ld64_step(const PixelState<2>& in, PixelState<2>& out, const Num<2>&
     t.s = (in.wre.s ^ in.wim.s) & mk.im_keep;
     // wre = wre2 - wim2 + c_re
     nw = in.wim2; nw.s = 1u;
-    add64_core(in.wre2, nw, u, f);
+    add64_core<WIDE>(in.wre2, nw, u, f);
     u.s &= ((uint32_t)out.iter & mk.re_and) ^ mk.re_xor;
-    add64_core(t, cim, out.wim, f);
-    add64_core(u, cre, out.wre, f);
+    add64_core<WIDE>(t, cim, out.wim, f);
+    add64_core<WIDE>(u, cre, out.wre, f);
     mul64_core(out.wim, out.wim, out.wim2, f);
     mul64_core(out.wre, out.wre, out.wre2, f);
     rare = ld64_flags_rare(f);
@@ -241,12 +264,20 @@ MDZ_HD bool pixel_step_spec<2>(PixelState<2>& st, const uint32_t* cre_m, const u
     return esc;
 }
 
-// two limbs have no separate wide variant: the step above already covers gaps up to 62 bits
+// level 2 at two limbs: the additions also take a far smaller or zero operand and deep cancellation
 template <>
 MDZ_HD bool pixel_step_spec_wide<2>(PixelState<2>& st, const uint32_t* cre_m, const uint32_t* cim_m,
                                     uint32_t* scr, const RoundCfg& rc, bool abs_im, int abs_re, uint32_t& rare_out)
 {
-    return pixel_step_spec<2>(st, cre_m, cim_m, scr, rc, abs_im, abs_re, rare_out);
+    bool rare = rc.ulp != 1u;
+    Num<2> cim, cre;
+    cim.m[0] = cim_m[0]; cim.m[1] = cim_m[kScratchStride]; cim.e = st.cim_e; cim.s = st.cim_s;
+    cre.m[0] = cre_m[0]; cre.m[1] = cre_m[kScratchStride]; cre.e = st.cre_e; cre.s = st.cre_s;
+    PixelState<2> out;
+    const bool esc = ld64_step<true>(st, out, cre, cim, scr, rc, ld64_masks(abs_im, abs_re), rare);
+    st = out;
+    rare_out |= rare ? 1u : 0u;
+    return esc;
 }
 
 }  // namespace mdz

@@ -18,6 +18,9 @@ def case(name, scale=1.0):
     w, h = int(960 * scale), int(540 * scale)
     if name == "ld":
         return config2(2 * w, 2 * h, 10000)
+    if name == "ldshift":
+        # config 2 moved by a fraction of a pixel: no column with x exactly 0, no row next to y = 0
+        return make_view("-0.4991", "0.0007", "4.0", 2 * w, 2 * h, mode="ld", depth=10000)
     if name.startswith("int"):
         # every pixel inside the main cardioid: `lanes` pixels that all run to depth (per-warp pace at a given occupancy)
         lanes = int(name[3:] or 113664)
