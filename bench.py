@@ -367,7 +367,7 @@ def main():
                                           "fp64_pct": ncu_num("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
                                           "issue_active_pct": ncu_num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                                           "source": "ncu capture of this kernel on this workload (profiles/r1_ncu_summary.json: ld64_cfg2)",
-                                          "why": "at 64 bits an iteration is 12 IMAD.WIDE against ~185 shift/compare/select/add "
+                                          "why": "at 64 bits an iteration is 12 IMAD.WIDE against ~170 shift/compare/select/add "
                                                  "instructions of alignment, normalisation and rounding: the ALU pipe binds, not the multiplier"},
                          "peak_imad32": peak32 / 1e12,
                          "frac_of_imad32_issue": kernel_rate * macs / peak32,
