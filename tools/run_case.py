@@ -18,6 +18,9 @@ def case(name, scale=1.0):
     w, h = int(960 * scale), int(540 * scale)
     if name == "ld":
         return config2(2 * w, 2 * h, 10000)
+    if name.startswith("cfg2p"):
+        # config 2's view (column x = 0, row y = 0 included) in MPFR mode at the given precision
+        return make_view("-0.5", "0.0", "4.0", w, h, precision=int(name[5:]), depth=10000)
     if name == "ldshift":
         # config 2 moved by a fraction of a pixel: no column with x exactly 0, no row next to y = 0
         return make_view("-0.4991", "0.0007", "4.0", 2 * w, 2 * h, mode="ld", depth=10000)
