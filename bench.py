@@ -33,12 +33,13 @@ def macs_per_iteration(n_limbs):
     return 2 * n_limbs * n_limbs + n_limbs
 
 
-def workload_cfg4():
-    """BASELINE configs[3] / the north star's target: a 1e-120 wide view at 512-bit MPFR,
-    3840x2160, depth 100000 (tests/views.py config4; every pixel escapes after ~12 800
-    iterations).  One image split across the ranks by interleaved bands: strong scaling."""
+def workload_cfg4(mode="mpfr"):
+    """BASELINE configs[3] / the north star's target: a 1e-120 wide view at 512 bits, 3840x2160,
+    depth 100000 (tests/views.py config4; every pixel escapes after ~12 800 iterations), in MPFR
+    mode (the north star's "512-bit MPFR-equivalent") or GMP mpf mode (as configs[3] names it).
+    One image split across the ranks by interleaved bands: strong scaling."""
     from views import config4
-    return config4(3840, 2160, 100000, mode="mpfr", precision=512)
+    return config4(3840, 2160, 100000, mode=mode, precision=512)
 
 
 def workload_view(world=1, scaling="weak"):
@@ -210,7 +211,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-side", action="store_true", help="skip the per-precision side measurements")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4", "cfg4gmp"],
                     help="cfg2 (default, the bench contract's workload): BASELINE configs[1]; cfg4: the north star's "
                          "target view, 3840x2160 at 512-bit MPFR, depth 100000, one image split over the ranks")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -241,11 +242,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    cfg4 = args.workload == "cfg4"
+    cfg4 = args.workload in ("cfg4", "cfg4gmp")
+    gmp4 = args.workload == "cfg4gmp"
     if cfg4:
         args.scaling = "strong"
         args.no_side = True
-    view = workload_cfg4() if cfg4 else workload_view(world, args.scaling)
+    view = workload_cfg4("gmp" if gmp4 else "mpfr") if cfg4 else workload_view(world, args.scaling)
     plan = mdz_b200.Plan(view, local, band_first=rank, band_stride=world)
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
@@ -330,17 +332,18 @@ def main():
             dram = ncu_num("dram__bytes_read.sum") + ncu_num("dram__bytes_write.sum")
         peak = mdz_b200.imad_peak(local, 200)                  # IMAD.WIDE.U32.X chains: 32x32->64 MAC/s
         peak32 = mdz_b200.imad_peak(local, 200, wide=False)    # 32-bit IMAD issue rate
-        macs = macs_per_iteration(ki["limbs"])
+        macs = macs_per_iteration(ki["limbs"] - 2 if view.mode == 2 else ki["limbs"])     # GMP mode multiplies the top P 64-bit limbs: N = 2P words
         kernel_rate = (total_iters / world) / (kernel_ms * 1e-3)        # this GPU's kernel alone
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": args.scaling if (world > 1 or cfg4) else "weak", "vs_baseline": None,
-            "dtype": ("16 x u32 significand + i32 exponent (soft-float == MPFR at 512 bits, round to nearest even)" if cfg4 else
+            "dtype": ("20 x u32 words (9 + 1 64-bit limbs) + limb exponent (soft-float == GMP 6.3 mpf at 512 bits, truncating)" if gmp4 else
+                      "16 x u32 significand + i32 exponent (soft-float == MPFR at 512 bits, round to nearest even)" if cfg4 else
                       "u64 significand + i32 exponent (soft-float == x87 long double, round to nearest even)"),
             "data": "synthetic",
-            "config": {"workload": ("BASELINE configs[3] / north-star target: 1e-120 wide view on M(23,2), 3840x2160, MPFR 512 bits, "
-                                    "depth 100000, one image split over %d GPU(s) (strong scaling)" % world) if cfg4 else
+            "config": {"workload": ("BASELINE configs[3] / north-star target: 1e-120 wide view on M(23,2), 3840x2160, %s 512 bits, "
+                                    "depth 100000, one image split over %d GPU(s) (strong scaling)" % ("GMP mpf" if gmp4 else "MPFR", world)) if cfg4 else
                                    "BASELINE configs[1]: full M-set cx=-0.5 cy=0 size=4, %dx%d, "
                                    "long double mode, depth 10000%s" % (
                                        view.real_width, view.real_height,
@@ -384,7 +387,8 @@ def main():
             # the 512-bit capture instead (profiles/r1_ncu_summary.json: mpfr512_seahorse_960x540)
             line["roofline"]["traffic"] = None
             line["roofline"].pop("traffic_note", None)
-            line["roofline"]["binding_pipe"] = {
+            line["roofline"]["binding_pipe"] = {"pipe": "fmaheavy + alu", "source": "no ncu capture of the GMP kernel this round",
+                                                "why": "escape_gmpf_kernel<20>: 666 MACs per iteration in full-schoolbook terms"} if gmp4 else {
                 "pipe": "fmaheavy + alu (issue-limited)", "source": "profiles/r1_ncu_summary.json: mpfr512_seahorse_960x540",
                 "why": "escape_mpfr_kernel<16>: 1281 issue slots per iteration of which 311 IMAD.WIDE; fmaheavy 57 %, ALU 54 %, "
                        "issue slots 51 % busy at 3 warps per scheduler (168 registers)"}
