@@ -402,7 +402,7 @@ def main():
             if cfg4:
                 lines = [(2 * k + 1) * view.real_height // (2 * cores) for k in range(cores)]    # one line per thread
                 rraw = refpath.ref_render_lines(lib, view, lines, cores)
-                sample_txt = "%d evenly spaced lines of the same 3840x2160 view, the reference's own MPFR line driver" % len(lines)
+                sample_txt = "%d evenly spaced lines of the same 3840x2160 view, the reference's own line driver" % len(lines)
                 sdepth = view.depth
                 same = bool(np.array_equal(rraw, raw[lines])) if world == 1 else None
             else:

@@ -38,6 +38,15 @@ inline void addsub128(uint32_t (&x)[4], uint32_t a1, uint32_t a2, uint32_t a3, c
     t = (uint64_t)a2 + (b[2] ^ mask) + c; x[2] = (uint32_t)t; c = t >> 32;
     t = (uint64_t)a3 + (b[3] ^ mask) + c; x[3] = (uint32_t)t;
 }
+// x = a - b over 128 bits (a0 == 0)
+inline void sub128(uint32_t (&x)[4], uint32_t a1, uint32_t a2, uint32_t a3, const uint32_t (&b)[4])
+{
+    uint64_t br = 0, t;
+    t = (uint64_t)0  - b[0] - br; x[0] = (uint32_t)t; br = (t >> 32) & 1u;
+    t = (uint64_t)a1 - b[1] - br; x[1] = (uint32_t)t; br = (t >> 32) & 1u;
+    t = (uint64_t)a2 - b[2] - br; x[2] = (uint32_t)t; br = (t >> 32) & 1u;
+    t = (uint64_t)a3 - b[3] - br; x[3] = (uint32_t)t;
+}
 #else
 // PTX shifts clamp the count at the register width, so a count of 64 gives 0
 MDZ_HD uint64_t shr64c(uint64_t x, uint32_t n) { uint64_t r; asm("shr.b64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n)); return r; }
@@ -66,6 +75,17 @@ MDZ_HD void addsub128(uint32_t (&x)[4], uint32_t a1, uint32_t a2, uint32_t a3, c
         "}" : "=&r"(x[0]), "=&r"(x[1]), "=&r"(x[2]), "=&r"(x[3]), "=&r"(junk)
             : "r"(mask & 1u), "r"(b[0] ^ mask), "r"(b[1] ^ mask), "r"(b[2] ^ mask), "r"(b[3] ^ mask),
               "r"(a1), "r"(a2), "r"(a3));
+}
+// a difference known to be one at compile time: one borrow chain, nothing to complement
+MDZ_HD void sub128(uint32_t (&x)[4], uint32_t a1, uint32_t a2, uint32_t a3, const uint32_t (&b)[4])
+{
+    asm("{\n\t"
+        "sub.cc.u32  %0, 0, %4;\n\t"
+        "subc.cc.u32 %1, %8, %5;\n\t"
+        "subc.cc.u32 %2, %9, %6;\n\t"
+        "subc.u32    %3, %10, %7;\n\t"
+        "}" : "=&r"(x[0]), "=&r"(x[1]), "=&r"(x[2]), "=&r"(x[3])
+            : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(a1), "r"(a2), "r"(a3));
 }
 #endif
 
@@ -142,7 +162,8 @@ MDZ_HD void mul64_spec(const Num<2>& a, const Num<2>& b, Num<2>& r, bool& rare)
 //    point on a diagonal, |wre| = |wim|, cancel wre^2 - wim^2 almost completely for ever).
 // On BASELINE configs[1] ~1 700 interior pixels of the first kind and 13 of the second used to run
 // the general step 10 000 times each, alone in their warps: the end of every render waited for them.
-template <bool WIDE = false>
+// SUBPOS: r = RN(a - b) for a, b >= 0 (wre^2 - wim^2), b's sign as given is ignored.
+template <bool WIDE = false, bool SUBPOS = false>
 MDZ_HD void add64_core(const Num<2>& a, const Num<2>& b, Num<2>& r, Ld64Flags& f)
 {
     const int32_t d = a.e - b.e;
@@ -163,10 +184,15 @@ MDZ_HD void add64_core(const Num<2>& a, const Num<2>& b, Num<2>& r, Ld64Flags& f
     const uint64_t BH = shr64c(Bm, ad + 1u), BL = shl64c(Bm, 63u - ad);
     const uint32_t sticky = (WIDE && ad > 65u) ? 1u : 0u;
     const uint32_t bw[4] = { (uint32_t)BL | sticky, (uint32_t)(BL >> 32), (uint32_t)BH, (uint32_t)(BH >> 32) };
-    const uint32_t mask = (a.s != b.s) ? 0xffffffffu : 0u;
     uint32_t x[4];
-    addsub128(x, A0 << 31, fsr(A0, A1, 1), A1 >> 1, bw, mask);
-    f.negor |= x[3] & mask;                                     // bit 127 is the sums' carry; a difference sets it only when negative
+    if (SUBPOS) {
+        sub128(x, A0 << 31, fsr(A0, A1, 1), A1 >> 1, bw);
+        f.negor |= x[3];
+    } else {
+        const uint32_t mask = (a.s != b.s) ? 0xffffffffu : 0u;
+        addsub128(x, A0 << 31, fsr(A0, A1, 1), A1 >> 1, bw, mask);
+        f.negor |= x[3] & mask;                                 // bit 127 is the sums' carry; a difference sets it only when negative
+    }
     // normalise.  31 or more cancelled bits (top word zero, about one addition in a million
     // on orbit data) are left to the general code: lz is then 32, the funnel shifts move
     // nothing, and the zero top word fails the top-bit test
@@ -182,7 +208,7 @@ MDZ_HD void add64_core(const Num<2>& a, const Num<2>& b, Num<2>& r, Ld64Flags& f
     // top bit clear: >= 31 bits cancelled / exact zero, or the increment carried out
     f.topand &= r.m[1];
     r.e = e - (int32_t)lz;
-    r.s = swap ? b.s : a.s;
+    r.s = SUBPOS ? (swap ? 1u : 0u) : (swap ? b.s : a.s);
 }
 template <bool WIDE = false>
 MDZ_HD void add64_spec(const Num<2>& a, const Num<2>& b, Num<2>& r, bool& rare)
@@ -216,14 +242,13 @@ MDZ_HD bool ld64_step(const PixelState<2>& in, PixelState<2>& out, const Num<2>&
     out.iter = in.iter + 1;
     out.cre_e = in.cre_e; out.cim_e = in.cim_e; out.cre_s = in.cre_s; out.cim_s = in.cim_s;
     Ld64Flags f; ld64_flags_init(f, rare);
-    Num<2> t, u, nw;
+    Num<2> t, u;
     // wim = 2*wre*wim + c_im
     mul64_core(in.wre, in.wim, t, f);
     t.e += 1;
     t.s = (in.wre.s ^ in.wim.s) & mk.im_keep;
     // wre = wre2 - wim2 + c_re
-    nw = in.wim2; nw.s = 1u;
-    add64_core<WIDE>(in.wre2, nw, u, f);
+    add64_core<WIDE, true>(in.wre2, in.wim2, u, f);
     u.s &= ((uint32_t)out.iter & mk.re_and) ^ mk.re_xor;
     add64_core<WIDE>(t, cim, out.wim, f);
     add64_core<WIDE>(u, cre, out.wre, f);

@@ -76,6 +76,12 @@ extern "C" int emu_ld64_op(int op, uint64_t am, int as, long ae, uint64_t bm, in
     if (bs == 0) set_zero(b); else { b.m[0] = (uint32_t)bm; b.m[1] = (uint32_t)(bm >> 32); b.e = (int32_t)be; b.s = bs < 0; }
     bool rare = false;
     if (op == 0) { mul64_spec(a, b, r, rare); r.s = a.s ^ b.s; }
+    else if (op == 6 || op == 7) {          // a - b for a, b >= 0 through the dedicated difference: plain / level 2
+        Ld64Flags f; ld64_flags_init(f, false);
+        a.s = 0; b.s = 0;
+        if (op == 6) add64_core<false, true>(a, b, r, f); else add64_core<true, true>(a, b, r, f);
+        rare = ld64_flags_rare(f);
+    }
     else if (op >= 4) { if (op == 5) b.s ^= 1u; add64_spec<true>(a, b, r, rare); }     // 4 / 5: add / sub, level-2 variant
     else { if (op == 3) b.s ^= 1u; add64_spec(a, b, r, rare); }
     *rm = ((uint64_t)r.m[1] << 32) | r.m[0]; *rs = r.s ? -1 : 1; *re = r.e;

@@ -222,6 +222,21 @@ def test_ld64_fast_ops_match_libmpfr_or_decline(emu):
                 b = Mpfr(prec).set_parts(rng.choice([1, -1]), ea, mb | (1 << 63))
         sa, ea, ma = a.parts()
         sb, eb, mb = b.parts()
+        if sa and sb:           # the dedicated difference of two non-negative values (wre^2 - wim^2)
+            pa, pb = Mpfr(prec).set_parts(1, ea, ma), Mpfr(prec).set_parts(1, eb, mb)
+            want = mpfr_op("sub", prec, pa, pb)
+            for op in (6, 7):
+                rm, rs, re_ = C.c_uint64(), C.c_int(), C.c_long()
+                rare = emu.emu_ld64_op(op, ma, 1, ea, mb, 1, eb, C.byref(rm), C.byref(rs), C.byref(re_))
+                if not rare:
+                    assert (rs.value, re_.value, rm.value) == want, ("subpos", op, pa.parts(), pb.parts(), want)
+                else:
+                    gap = abs(ea - eb)
+                    lost = max(ea, eb) - want[1] if want[0] else 999
+                    if op == 6:
+                        assert gap > 62 or lost >= 31 or want[2] == 1 << 63, ("subpos declined", pa.parts(), pb.parts(), want)
+                    else:
+                        assert 64 <= gap <= 65 or lost >= 63 or want[2] == 1 << 63, ("subpos level 2 declined", pa.parts(), pb.parts(), want)
         for op, name in ((0, "mul"), (2, "add"), (3, "sub"), (4, "add"), (5, "sub")):
             rm, rs, re_ = C.c_uint64(), C.c_int(), C.c_long()
             rare = emu.emu_ld64_op(op, ma, sa, ea, mb, sb, eb, C.byref(rm), C.byref(rs), C.byref(re_))
