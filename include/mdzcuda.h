@@ -104,6 +104,17 @@ int mdzcuda_plan_tune(mdzcuda_plan*, int chunk_iters, int blocks_per_sm);
  */
 int mdzcuda_plan_set_cycle_detection(mdzcuda_plan*, int on);
 
+/* Tail compaction ("parking").  The render becomes two launches of the same kernel:
+ * the first stops when the pixel queue runs dry and writes the state of every pixel still in
+ * flight to device memory; the second resumes them, 32 per warp, spread evenly over the SMs.  It
+ * pays when the plan's image is only a few times the persistent grid -- one GPU's share of a
+ * strong-scaled render -- where the last generation of long-running pixels would otherwise occupy
+ * every warp sparsely.  The state is carried over bit for bit: raw_data is identical with it on or
+ * off.  mode: -1 automatic (MDZCUDA_PARK=0/1 overrides), 0 off, 1 on.  Long double and MPFR modes.
+ * Scheduling only: the reference hands out whole lines under a mutex (src/render_threads.c:360-393)
+ * and has no counterpart. */
+int mdzcuda_plan_set_parking(mdzcuda_plan*, int mode);
+
 /* Enqueue the reset + escape-time kernel on `cuda_stream` (a cudaStream_t; NULL
  * = the legacy default stream).  Asynchronous. */
 int mdzcuda_plan_launch(mdzcuda_plan*, void* cuda_stream);

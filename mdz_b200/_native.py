@@ -51,6 +51,7 @@ SYMBOLS = {
     "mdzcuda_plan_create": (C.c_void_p, [C.POINTER(View), C.c_int, C.c_int, C.c_int]),
     "mdzcuda_plan_tune": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mdzcuda_plan_set_cycle_detection": (C.c_int, [C.c_void_p, C.c_int]),
+    "mdzcuda_plan_set_parking": (C.c_int, [C.c_void_p, C.c_int]),
     "mdzcuda_plan_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mdzcuda_plan_wait": (C.c_int, [C.c_void_p]),
     "mdzcuda_plan_cancel": (C.c_int, [C.c_void_p]),

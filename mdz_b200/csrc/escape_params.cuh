@@ -42,6 +42,17 @@ struct EscapeParams {
     int cycle;              // 1: exact periodicity check (escape_kernel.cuh); MPFR / long double kernels only
     uint32_t* cycle_scratch;    // [2N+3][grid threads] saved states, when cycle != 0
     ColourParams colour;    // fused epilogue: colour a band as soon as it completes (enabled = 0: raw only)
+    // Tail compaction (escape_kernel.cuh "Parking"): phase 0 stops when the pixel queue runs dry and
+    // writes the state of the pixels still in flight to park_buf; phase 1 -- a second launch of the
+    // same kernel -- resumes them, 32 per warp.  park_cap = 0: off (one launch does everything).
+    int phase;                      // 0: pixels come from the queue; 1: from the parked list
+    unsigned int park_cap;          // entries the list holds (= threads of the grid)
+    unsigned int* park_count;       // [0] entries parked, [1] phase 1's queue counter
+    uint32_t* park_buf;             // [ParkWords][park_cap]
+    const unsigned int* park_perm;  // phase 1 reads the list in this order: by iteration count (park_sort_kernel)
+    unsigned int* park_smslot;      // [4096] phase 1: arrivals per SM, dense SM numbers   } zeroed by
+    unsigned int* park_claimed;     // [park_cap / 32] phase 1: group of 32 handed out      } park_sort_kernel
+    int park_sms;                   // SMs of the device
     Ld64Masks ld_masks;     // ld64_masks(fractal), filled in by the host so that the hot loop reads them as constants
 };
 

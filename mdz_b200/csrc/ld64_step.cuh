@@ -29,6 +29,13 @@ inline void round_rne64(uint32_t& m0, uint32_t& m1, uint32_t h0, uint32_t h1, ui
     const uint64_t m = h + (l > 0x8000000000000000ull ? 1u : 0u);
     m0 = (uint32_t)m; m1 = (uint32_t)(m >> 32);
 }
+// the same, with the carry out of the increment (the significand was all ones: it is now 0)
+inline void round_rne64c(uint32_t& m0, uint32_t& m1, uint32_t& c, uint32_t h0, uint32_t h1, uint32_t l0, uint32_t l1)
+{
+    const uint64_t h = ((uint64_t)h1 << 32) | h0, l = (((uint64_t)l1 << 32) | l0) | (h & 1u);
+    const uint64_t m = h + (l > 0x8000000000000000ull ? 1u : 0u);
+    m0 = (uint32_t)m; m1 = (uint32_t)(m >> 32); c = m < h ? 1u : 0u;
+}
 // x = a + (b ^ mask) + (mask & 1) over 128 bits (a0 == 0)
 inline void addsub128(uint32_t (&x)[4], uint32_t a1, uint32_t a2, uint32_t a3, const uint32_t (&b)[4], uint32_t mask)
 {
@@ -62,6 +69,18 @@ MDZ_HD void round_rne64(uint32_t& m0, uint32_t& m1, uint32_t h0, uint32_t h1, ui
         "addc.cc.u32 %0, %5, 0;\n\t"
         "addc.u32    %1, %6, 0;\n\t"
         "}" : "=&r"(m0), "=&r"(m1), "=&r"(junk) : "r"(w0), "r"(l1), "r"(h0), "r"(h1));
+}
+MDZ_HD void round_rne64c(uint32_t& m0, uint32_t& m1, uint32_t& c, uint32_t h0, uint32_t h1, uint32_t l0, uint32_t l1)
+{
+    const uint32_t w0 = l0 | (h0 & 1u);
+    uint32_t junk;
+    asm("{\n\t"
+        "add.cc.u32  %3, %4, 0xffffffff;\n\t"
+        "addc.cc.u32 %3, %5, 0x7fffffff;\n\t"
+        "addc.cc.u32 %0, %6, 0;\n\t"
+        "addc.cc.u32 %1, %7, 0;\n\t"
+        "addc.u32    %2, 0, 0;\n\t"
+        "}" : "=&r"(m0), "=&r"(m1), "=&r"(c), "=&r"(junk) : "r"(w0), "r"(l1), "r"(h0), "r"(h1));
 }
 MDZ_HD void addsub128(uint32_t (&x)[4], uint32_t a1, uint32_t a2, uint32_t a3, const uint32_t (&b)[4], uint32_t mask)
 {
@@ -120,6 +139,10 @@ MDZ_HD bool ld64_flags_rare(const Ld64Flags& f) { return f.rare || (int32_t)(~f.
 // r = RN(a * b): the sign is left to the caller.  A product just below a power of two
 // (top bit at 126, all ones after the one-bit shift) can round up past 2^64; the top-bit
 // test catches that and a zero operand.
+// WIDE (level 2): an exactly zero factor gives an exact zero, and a product that rounds up to the next
+// power of two is renormalised instead of declined -- a converged orbit can sit on either for ever
+// (c = -1: wre is 0 every other iteration; c = 1/4 + i/8: wre * wim rounds up to 1/8 at the fixed point).
+template <bool WIDE = false>
 MDZ_HD void mul64_core(const Num<2>& a, const Num<2>& b, Num<2>& r, Ld64Flags& f)
 {
     // (Measured alternative, rejected: limb_ops.cuh mul_full<2> -- aligned accumulator pairs, no
@@ -132,15 +155,27 @@ MDZ_HD void mul64_core(const Num<2>& a, const Num<2>& b, Num<2>& r, Ld64Flags& f
     const uint32_t p0 = (uint32_t)p00, p1 = (uint32_t)u, p2 = (uint32_t)hi, p3 = (uint32_t)(hi >> 32);
     const uint32_t sh = top_clear(p3);               // top bit at 127 or 126
     const uint32_t x3 = fsl(p2, p3, sh), x2 = fsl(p1, p2, sh), x1 = fsl(p0, p1, sh), x0 = p0 << sh;
-    round_rne64(r.m[0], r.m[1], x2, x3, x0, x1);
-    r.e = a.e + b.e - (int32_t)sh;
-    f.topand &= r.m[1];
-    f.rare = f.rare || r.e < E_MIN;
+    if (WIDE) {
+        uint32_t c;
+        round_rne64c(r.m[0], r.m[1], c, x2, x3, x0, x1);
+        r.m[1] |= c << 31;
+        const bool z = a.m[1] == 0u || b.m[1] == 0u;
+        const int32_t e = a.e + b.e - (int32_t)sh + (int32_t)c;
+        f.rare = f.rare || (!z && e < E_MIN);
+        r.e = z ? E_ZERO : e;
+        f.topand &= r.m[1] | (z ? 0x80000000u : 0u);
+    } else {
+        round_rne64(r.m[0], r.m[1], x2, x3, x0, x1);
+        r.e = a.e + b.e - (int32_t)sh;
+        f.topand &= r.m[1];
+        f.rare = f.rare || r.e < E_MIN;
+    }
 }
+template <bool WIDE = false>
 MDZ_HD void mul64_spec(const Num<2>& a, const Num<2>& b, Num<2>& r, bool& rare)
 {
     Ld64Flags f; ld64_flags_init(f, rare);
-    mul64_core(a, b, r, f);
+    mul64_core<WIDE>(a, b, r, f);
     rare = ld64_flags_rare(f);
 }
 
@@ -204,10 +239,20 @@ MDZ_HD void add64_core(const Num<2>& a, const Num<2>& b, Num<2>& r, Ld64Flags& f
     }
     const uint32_t lz = (uint32_t)clz32(x[3]);
     const uint32_t h1 = fsl(x[2], x[3], lz), h0 = fsl(x[1], x[2], lz), l1 = fsl(x[0], x[1], lz), l0 = x[0] << lz;
+    if (WIDE) {
+        // level 2 also keeps an exactly zero result and a rounding increment that carries out
+        uint32_t c;
+        round_rne64c(r.m[0], r.m[1], c, h0, h1, l0, l1);
+        r.m[1] |= c << 31;
+        const bool z = (x[0] | x[1] | x[2] | x[3]) == 0u;
+        f.topand &= r.m[1] | (z ? 0x80000000u : 0u);
+        r.e = z ? E_ZERO : e - (int32_t)lz + (int32_t)c;
+    } else {
     round_rne64(r.m[0], r.m[1], h0, h1, l0, l1);
     // top bit clear: >= 31 bits cancelled / exact zero, or the increment carried out
     f.topand &= r.m[1];
     r.e = e - (int32_t)lz;
+    }
     r.s = SUBPOS ? (swap ? 1u : 0u) : (swap ? b.s : a.s);
 }
 template <bool WIDE = false>
@@ -244,7 +289,7 @@ MDZ_HD bool ld64_step(const PixelState<2>& in, PixelState<2>& out, const Num<2>&
     Ld64Flags f; ld64_flags_init(f, rare);
     Num<2> t, u;
     // wim = 2*wre*wim + c_im
-    mul64_core(in.wre, in.wim, t, f);
+    mul64_core<WIDE>(in.wre, in.wim, t, f);
     t.e += 1;
     t.s = (in.wre.s ^ in.wim.s) & mk.im_keep;
     // wre = wre2 - wim2 + c_re
@@ -252,8 +297,8 @@ MDZ_HD bool ld64_step(const PixelState<2>& in, PixelState<2>& out, const Num<2>&
     u.s &= ((uint32_t)out.iter & mk.re_and) ^ mk.re_xor;
     add64_core<WIDE>(t, cim, out.wim, f);
     add64_core<WIDE>(u, cre, out.wre, f);
-    mul64_core(out.wim, out.wim, out.wim2, f);
-    mul64_core(out.wre, out.wre, out.wre2, f);
+    mul64_core<WIDE>(out.wim, out.wim, out.wim2, f);
+    mul64_core<WIDE>(out.wre, out.wre, out.wre2, f);
     rare = ld64_flags_rare(f);
     out.wim2.s = 0; out.wre2.s = 0;
     const int32_t emax = out.wim2.e > out.wre2.e ? out.wim2.e : out.wre2.e;

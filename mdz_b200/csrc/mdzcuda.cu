@@ -331,7 +331,7 @@ struct mdzcuda_plan {
     RoundCfg rc;
     int32_t* d_raw = nullptr;
     uint32_t* d_arena = nullptr;        // tables + everything below
-    unsigned int* d_ctrl = nullptr;     // [0] queue, [1] bands_done
+    unsigned int* d_ctrl = nullptr;     // [0] queue, [1] bands_done, [2] parked pixels, [3] phase 1's queue
     unsigned int* d_band_count = nullptr;
     unsigned int* d_band_flag = nullptr;    // [nbands] generation of the launch that completed the band
     unsigned int gen = 0;                   // generation of the current launch (1, 2, ...; never 0)
@@ -345,6 +345,9 @@ struct mdzcuda_plan {
     int cycle = 0;                      // exact periodicity check (mdzcuda_plan_set_cycle_detection)
     uint32_t* d_cycle = nullptr;        // its saved-state columns, allocated at the first launch that needs them
     size_t cycle_words = 0;
+    int park = -1;                      // tail compaction (escape_kernel.cuh "Parking"): -1 automatic, 0 off, 1 on
+    uint32_t* d_park = nullptr;         // parked pixel states + reading order + claim words, allocated at the first launch that parks
+    size_t park_words = 0;
     bool gmp = false;
     mdzcuda_kernel_info info;
     unsigned int* h_pinned = nullptr;   // 4 words of pinned staging
@@ -591,7 +594,7 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
             arena_put(ar, xs, o[0], o[1], o[2]);
             arena_put(ar, ys, o[3], o[4], o[5]);
             const size_t table_words = arena_put(ar, jc, o[6], o[7], o[8]);
-            const size_t o_ctrl = ar.reserve(4);
+            const size_t o_ctrl = ar.reserve(8);
             const size_t o_count = ar.reserve((size_t)pl->nbands + 1);
             const size_t o_flag = ar.reserve((size_t)pl->nbands + 1);
             const size_t o_cancel = ar.reserve(4);
@@ -644,6 +647,52 @@ extern "C" int mdzcuda_plan_set_cycle_detection(mdzcuda_plan* pl, int on)
 {
     if (!pl) { set_err("null plan"); return 0; }
     pl->cycle = on ? 1 : 0;
+    return 1;
+}
+
+// Order in which phase 1 reads the parked list: a counting sort by iteration count (2048 buckets over
+// 0..depth), one block.  Pixels that entered the list with about the same count have about the same
+// number of iterations left -- exactly so for those that never escape -- and end up in the same warps,
+// which then finish, and leave the SM to the others, as a whole.  Also zeroes phase 1's claim words.
+__global__ void __launch_bounds__(1024)
+park_sort_kernel(const unsigned int* park_count, const uint32_t* iters, unsigned int* perm, int depth,
+                 unsigned int* zero, unsigned int zero_words)
+{
+    __shared__ unsigned int hist[2048];
+    __shared__ unsigned int part[1024];
+    const unsigned n = park_count[0];
+    const unsigned t = threadIdx.x;
+    for (unsigned i = t; i < zero_words; i += 1024) zero[i] = 0u;
+    hist[t] = 0u; hist[t + 1024] = 0u;
+    __syncthreads();
+    const unsigned long long scale = ((unsigned long long)2048 << 32) / (unsigned long long)(depth > 0 ? depth : 1);
+    for (unsigned i = t; i < n; i += 1024) {
+        const unsigned b = (unsigned)(((unsigned long long)iters[i] * scale) >> 32);
+        atomicAdd(&hist[b < 2047u ? b : 2047u], 1u);
+    }
+    __syncthreads();
+    const unsigned a0 = hist[2 * t], a1 = hist[2 * t + 1];
+    part[t] = a0 + a1;
+    __syncthreads();
+    for (unsigned d = 1; d < 1024; d <<= 1) {
+        const unsigned v = t >= d ? part[t - d] : 0u;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    const unsigned before = part[t] - (a0 + a1);
+    hist[2 * t] = before; hist[2 * t + 1] = before + a0;
+    __syncthreads();
+    for (unsigned i = t; i < n; i += 1024) {
+        const unsigned b = (unsigned)(((unsigned long long)iters[i] * scale) >> 32);
+        perm[atomicAdd(&hist[b < 2047u ? b : 2047u], 1u)] = i;
+    }
+}
+
+extern "C" int mdzcuda_plan_set_parking(mdzcuda_plan* pl, int mode)
+{
+    if (!pl) { set_err("null plan"); return 0; }
+    pl->park = mode < 0 ? -1 : (mode ? 1 : 0);
     return 1;
 }
 
@@ -727,8 +776,44 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
             }
             p.cycle_scratch = pl->d_cycle;
         }
+        // Tail compaction: a second launch for the pixels still in flight when the queue runs dry
+        // (DESIGN.md 4.3).  It pays when this plan's last generation of long-running pixels is sparse --
+        // one GPU's share of a strong-scaled render: 14.5 -> 9.8 ms on an eighth of config 2 -- and is
+        // neutral when it is dense; not worth the launches for images below twice the grid.
+        // MDZCUDA_PARK=0 / 1 or mdzcuda_plan_set_parking force it off / on.
+        p.phase = 0; p.park_cap = 0; p.park_count = pl->d_ctrl + 2; p.park_buf = nullptr; p.park_perm = nullptr;
+        p.park_smslot = nullptr; p.park_claimed = nullptr; p.park_sms = 1;
+        static const int park_env = [] { const char* e = getenv("MDZCUDA_PARK"); return e && *e ? atoi(e) : -1; }();
+        const int park_mode = pl->park >= 0 ? pl->park : park_env;
+        const bool park = !pl->gmp && (park_mode > 0 || (park_mode < 0 && npx >= 2 * grid * kBlock));
+        if (park) {
+            const size_t cap = (size_t)grid * kBlock;
+            const size_t state_words = (size_t)(6 * pl->n32 + 9) * cap;
+            const size_t claim_words = 4096 + (cap + 31) / 32;
+            const size_t words = state_words + cap + claim_words;
+            if (words > pl->park_words) {
+                if (pl->d_park) { CUDA_OK(cudaStreamSynchronize(st)); pool_free(pl->device, pl->d_park); pl->d_park = nullptr; pl->park_words = 0; }
+                CUDA_OK(pool_alloc(pl->device, (void**)&pl->d_park, words * sizeof(uint32_t)));
+                pl->park_words = words;
+            }
+            p.park_cap = (unsigned int)cap;
+            p.park_buf = pl->d_park;
+            p.park_perm = pl->d_park + state_words;
+            p.park_smslot = pl->d_park + state_words + cap;
+            p.park_claimed = p.park_smslot + 4096;
+            p.park_sms = ki.sm_count > 0 ? ki.sm_count : 1;
+        }
         fn<<<(unsigned)grid, kBlock, ki.shared_bytes, st>>>(p);
         CUDA_OK(cudaGetLastError());
+        if (park) {
+            p.phase = 1;
+            park_sort_kernel<<<1, 1024, 0, st>>>(p.park_count, p.park_buf + (size_t)(6 * pl->n32 + 7) * p.park_cap,
+                                                 (unsigned int*)p.park_perm, p.depth, p.park_smslot,
+                                                 (unsigned int)(4096 + ((size_t)p.park_cap + 31) / 32));
+            CUDA_OK(cudaGetLastError());
+            fn<<<(unsigned)grid, kBlock, ki.shared_bytes, st>>>(p);
+            CUDA_OK(cudaGetLastError());
+        }
     }
     CUDA_OK(cudaEventRecord(pl->done_ev, st));
     return 1;
@@ -886,7 +971,7 @@ extern "C" void mdzcuda_plan_destroy(mdzcuda_plan* pl)
     if (pl->side) cudaStreamSynchronize(pl->side);
     DevPool& P = g_pool[pl->device];
     pool_free(pl->device, pl->d_palette); pool_free(pl->device, pl->d_rgb);
-    pool_free(pl->device, pl->d_raw); pool_free(pl->device, pl->d_arena); pool_free(pl->device, pl->d_cycle);
+    pool_free(pl->device, pl->d_raw); pool_free(pl->device, pl->d_arena); pool_free(pl->device, pl->d_cycle); pool_free(pl->device, pl->d_park);
     {
         std::lock_guard<std::mutex> lock(P.mu);
         if (pl->side) P.streams.push_back(pl->side);

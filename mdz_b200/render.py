@@ -114,6 +114,10 @@ class Plan:
         """Exact periodicity check: same raw_data, interior pixels finish early."""
         self._chk(_l.lib.mdzcuda_plan_set_cycle_detection(self.h, 1 if on else 0), "plan_set_cycle_detection")
 
+    def set_parking(self, mode=-1):
+        """Tail compaction: -1 automatic, 0 off, 1 on.  Same raw_data either way."""
+        self._chk(_l.lib.mdzcuda_plan_set_parking(self.h, mode), "plan_set_parking")
+
     def launch(self, stream=None):
         self._chk(_l.lib.mdzcuda_plan_launch(self.h, C.c_void_p(stream or 0)), "plan_launch")
 

@@ -76,6 +76,7 @@ extern "C" int emu_ld64_op(int op, uint64_t am, int as, long ae, uint64_t bm, in
     if (bs == 0) set_zero(b); else { b.m[0] = (uint32_t)bm; b.m[1] = (uint32_t)(bm >> 32); b.e = (int32_t)be; b.s = bs < 0; }
     bool rare = false;
     if (op == 0) { mul64_spec(a, b, r, rare); r.s = a.s ^ b.s; }
+    else if (op == 8) { mul64_spec<true>(a, b, r, rare); r.s = a.s ^ b.s; }       // level 2 product
     else if (op == 6 || op == 7) {          // a - b for a, b >= 0 through the dedicated difference: plain / level 2
         Ld64Flags f; ld64_flags_init(f, false);
         a.s = 0; b.s = 0;

@@ -1,6 +1,8 @@
 """GPU parity: iteration counts from libmdzcuda (through its C ABI) against the
 unmodified reference hot path (oracle/_ref/libmdzref.so) on the same views.
 Bit-exact for the long double and MPFR modes."""
+import os
+
 import numpy as np
 import pytest
 
@@ -191,6 +193,64 @@ def test_cycle_detection_changes_nothing(ref_lib, name, mk):
         bad = np.argwhere(got != want)
         assert bad.size == 0, "%s spec=%d: %d mismatching pixels, first %s: got %d want %d" % (
             name, spec, len(bad), bad[0], got[tuple(bad[0])], want[tuple(bad[0])])
+
+
+@pytest.mark.parametrize("name,mk", CYCLE_VIEWS, ids=[c[0] for c in CYCLE_VIEWS])
+def test_tail_compaction_changes_nothing(ref_lib, name, mk):
+    """Parking (mdzcuda_plan_set_parking): the first launch stops when the queue runs dry and
+    writes the live pixels' state to HBM, the second resumes them.  Forced on -- these views are
+    smaller than the grid, so everything is parked after its first chunk -- raw_data must equal the
+    reference's, with and without the periodicity check, whole and as one rank's share."""
+    v = mk()
+    want, _ = ref_render(ref_lib, v)
+    for cyc in (False, True):
+        p = mdz_b200.Plan(v, 0)
+        p.set_parking(1)
+        p.set_cycle_detection(cyc)
+        got = p.run()
+        p.close()
+        bad = np.argwhere(got != want)
+        assert bad.size == 0, "%s cyc=%d: %d mismatching pixels, first %s: got %d want %d" % (
+            name, cyc, len(bad), bad[0], got[tuple(bad[0])], want[tuple(bad[0])])
+    out = np.full_like(want, -1)
+    plans = [mdz_b200.Plan(v, 0, first, 2) for first in range(2)]
+    for p in plans:
+        p.set_parking(1)
+        p.run(out)
+        p.close()
+    assert np.array_equal(out, want)
+
+
+LEVEL2_VIEWS = [
+    # long double mode, pixels on which the plain fast iteration declines for ever (DESIGN.md 4.3): the
+    # column x = 0 and the row y = 0 (zero operands), rows next to the real axis (100-bit gaps), fixed
+    # points on a diagonal (wre^2 - wim^2 cancels), c = -1 (wre is 0 every other iteration), c = 1/4 + i/8
+    # (wre * wim rounds up to a power of two at the fixed point)
+    ("axes through the image", lambda: make_view("0", "0", "3.2", 128, 96, mode="ld", depth=3000)),
+    ("cfg2 grid (dyadic c)", lambda: config2(480, 270, 3000)),
+    ("next to the real axis", lambda: make_view("-0.5", "1e-17", "3.0", 96, 65, mode="ld", depth=2500)),
+    ("ship axes", lambda: make_view("0", "0", "3.2", 96, 72, mode="ld", depth=1500, fractal=BURNING_SHIP)),
+    ("celtic axes", lambda: make_view("0", "0", "3.2", 96, 72, mode="ld", depth=1500, fractal=GENERALIZED_CELTIC)),
+    ("hybrid axes", lambda: make_view("0", "0", "3.2", 96, 72, mode="ld", depth=1500, fractal=VARIANT)),
+    ("julia c = -1", lambda: make_view("0", "0", "3.2", 96, 72, mode="ld", depth=2000, family=FAMILY_JULIA, julia=("-1", "0"))),
+    ("julia c = 1/4 + i/8", lambda: make_view("0", "0", "3.2", 96, 72, mode="ld", depth=2000, family=FAMILY_JULIA, julia=("0.25", "0.125"))),
+]
+
+
+@pytest.mark.parametrize("name,mk", LEVEL2_VIEWS, ids=[c[0] for c in LEVEL2_VIEWS])
+def test_long_double_level_two_pixels_match_reference(ref_lib, name, mk):
+    """Views dense in the operands only level 2 of the long double iteration takes
+    (ld64_step.cuh add64_core<true> / mul64_core<true>); the warps get there by themselves."""
+    v = mk()
+    want, _ = ref_render(ref_lib, v)
+    for park in (0, 1):
+        p = mdz_b200.Plan(v, 0)
+        p.set_parking(park)
+        got = p.run()
+        p.close()
+        bad = np.argwhere(got != want)
+        assert bad.size == 0, "%s park=%d: %d mismatching pixels, first %s: got %d want %d" % (
+            name, park, len(bad), bad[0], got[tuple(bad[0])], want[tuple(bad[0])])
 
 
 def test_delivery_never_runs_ahead_of_the_kernel(ref_lib):

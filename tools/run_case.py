@@ -49,12 +49,15 @@ ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--chunk", type=int, default=0)
 ap.add_argument("--bps", type=int, default=0)
 ap.add_argument("--cycle", type=int, default=0, help="1: exact periodicity check on")
+ap.add_argument("--park", type=int, default=-1, help="tail compaction: -1 automatic, 0 off, 1 on")
 ap.add_argument("--stride", type=int, default=1, help="render bands 0, stride, 2*stride, ... only (one rank's share of a strong-scaled render)")
 a = ap.parse_args()
 v = case(a.case, a.scale)
 plan = mdz_b200.Plan(v, 0, 0, a.stride)
 plan.tune(a.chunk, a.bps)
 plan.set_cycle_detection(bool(a.cycle))
+if a.park != -1:
+    plan.set_parking(a.park)
 for i in range(a.reps):
     t0 = time.perf_counter()
     plan.launch()
