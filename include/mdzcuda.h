@@ -110,10 +110,15 @@ int mdzcuda_plan_set_cycle_detection(mdzcuda_plan*, int on);
  * pays when the plan's image is only a few times the persistent grid -- one GPU's share of a
  * strong-scaled render -- where the last generation of long-running pixels would otherwise occupy
  * every warp sparsely.  The state is carried over bit for bit: raw_data is identical with it on or
- * off.  mode: -1 automatic (MDZCUDA_PARK=0/1 overrides), 0 off, 1 on.  Long double and MPFR modes.
+ * off.  mode: -1 automatic (MDZCUDA_PARK=0/1 overrides), 0 off, 1 on.  Compiled into the long double and MPFR kernels of up to 128 bits (4 limbs); a no-op for wider ones and in GMP mode.
  * Scheduling only: the reference hands out whole lines under a mutex (src/render_threads.c:360-393)
  * and has no counterpart. */
 int mdzcuda_plan_set_parking(mdzcuda_plan*, int mode);
+
+/* Kernels this plan has launched so far (escape-time launches count 1, or 3 with parking:
+ * phase 0, the ordering pass, phase 1; a recolour counts 1).  For reports (bench.py's
+ * gpu_launches); -1 on a null plan. */
+int mdzcuda_plan_kernels_launched(mdzcuda_plan*);
 
 /* Enqueue the reset + escape-time kernel on `cuda_stream` (a cudaStream_t; NULL
  * = the legacy default stream).  Asynchronous. */

@@ -52,6 +52,7 @@ SYMBOLS = {
     "mdzcuda_plan_tune": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mdzcuda_plan_set_cycle_detection": (C.c_int, [C.c_void_p, C.c_int]),
     "mdzcuda_plan_set_parking": (C.c_int, [C.c_void_p, C.c_int]),
+    "mdzcuda_plan_kernels_launched": (C.c_int, [C.c_void_p]),
     "mdzcuda_plan_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mdzcuda_plan_wait": (C.c_int, [C.c_void_p]),
     "mdzcuda_plan_cancel": (C.c_int, [C.c_void_p]),

@@ -89,6 +89,11 @@ template <int N> struct MinBlocks {
 // raw_data does not depend on any of this.
 // ---------------------------------------------------------------------------
 template <int N> struct ParkWords { static constexpr int value = 6 * N + 9; };
+// Compiled in for N <= 4 only (long double, MPFR to 128 bits): in the wider kernels the two extra
+// paths cost registers the hot loop has no room for (N = 10: spill stores 32 -> 136 bytes, MPFR-320
+// 15.1 -> 13.6 G it/s on the B200), and the deep views those precisions are for keep every lane busy
+// to the end (configs[3] splits over eight GPUs at 99 %).  mdzcuda.cu parks only plans with n32 <= kParkMaxLimbs.
+template <int N> struct Parkable { static constexpr bool value = N <= kParkMaxLimbs; };
 
 template <int N>
 __device__ __forceinline__ void park_store(uint32_t* col, size_t stride, const PixelState<N>& st,
@@ -276,8 +281,10 @@ escape_mpfr_kernel(const EscapeParams p)
     uint32_t* ckpt = csm + (2 * N + ScratchWords<N>::value) * kBlock + threadIdx.x;   // only used when SpecSmemCkpt<N>
 
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned total = p.phase ? __ldcg(&p.park_count[0]) : (unsigned)p.width * (unsigned)p.lines;
-    const bool parking = p.park_cap != 0u && p.phase == 0;
+    constexpr bool kPark = Parkable<N>::value;
+    const bool phase1 = kPark && p.phase != 0;
+    const unsigned total = phase1 ? __ldcg(&p.park_count[0]) : (unsigned)p.width * (unsigned)p.lines;
+    const bool parking = kPark && p.park_cap != 0u && p.phase == 0;
 
     PixelState<N> st;
     set_zero(st.wre); set_zero(st.wim); set_zero(st.wre2); set_zero(st.wim2);
@@ -308,14 +315,14 @@ escape_mpfr_kernel(const EscapeParams p)
             }
             ctl = __shfl_sync(0xffffffffu, ctl, 0);
             if (ctl & 1u) break;
-            if (ctl & 2u) {
+            if constexpr (kPark) if (ctl & 2u) {
                 // the queue is dry: hand what is still in flight to phase 1
                 park_lanes<N>(p, active, lane, st, cre_m, cim_m, pix);
                 break;
             }
         }
         // ---- refill finished lanes from the queue ------------------------
-        if (p.phase) {
+        if (phase1) { if constexpr (kPark) {
             // Phase 1: a warp takes 32 consecutive entries of the sorted list at a time and the next 32
             // once all of them are done.  A short list must not end up on the SMs whose blocks happened
             // to start first, so the first claim goes by position: the k-th warp to arrive on the d-th SM
@@ -358,7 +365,7 @@ escape_mpfr_kernel(const EscapeParams p)
                     }
                 }
             }
-        } else
+        } } else
         if (!exhausted) {
             const unsigned need = __ballot_sync(0xffffffffu, !active);
             if (need) {

@@ -19,6 +19,10 @@ struct CoordTable {
     int count;
 };
 
+// Tail compaction is compiled into the kernels of at most this many limbs (escape_kernel.cuh Parkable)
+// and mdzcuda.cu parks only plans of such kernels.
+constexpr int kParkMaxLimbs = 4;
+
 struct EscapeParams {
     CoordTable xs;          // real_width entries: x[ix]      (fractal.c:183-186)
     CoordTable ys;          // one entry per local line: y[line] (fractal.c:167-170)

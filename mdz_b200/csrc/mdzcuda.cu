@@ -345,6 +345,7 @@ struct mdzcuda_plan {
     int cycle = 0;                      // exact periodicity check (mdzcuda_plan_set_cycle_detection)
     uint32_t* d_cycle = nullptr;        // its saved-state columns, allocated at the first launch that needs them
     size_t cycle_words = 0;
+    int kernels_launched = 0;           // kernels this plan has put on a stream so far (mdzcuda_plan_kernels_launched)
     int park = -1;                      // tail compaction (escape_kernel.cuh "Parking"): -1 automatic, 0 off, 1 on
     uint32_t* d_park = nullptr;         // parked pixel states + reading order + claim words, allocated at the first launch that parks
     size_t park_words = 0;
@@ -689,6 +690,12 @@ park_sort_kernel(const unsigned int* park_count, const uint32_t* iters, unsigned
     }
 }
 
+extern "C" int mdzcuda_plan_kernels_launched(mdzcuda_plan* pl)
+{
+    if (!pl) { set_err("null plan"); return -1; }
+    return pl->kernels_launched;
+}
+
 extern "C" int mdzcuda_plan_set_parking(mdzcuda_plan* pl, int mode)
 {
     if (!pl) { set_err("null plan"); return 0; }
@@ -785,7 +792,7 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         p.park_smslot = nullptr; p.park_claimed = nullptr; p.park_sms = 1;
         static const int park_env = [] { const char* e = getenv("MDZCUDA_PARK"); return e && *e ? atoi(e) : -1; }();
         const int park_mode = pl->park >= 0 ? pl->park : park_env;
-        const bool park = !pl->gmp && (park_mode > 0 || (park_mode < 0 && npx >= 2 * grid * kBlock));
+        const bool park = !pl->gmp && pl->n32 <= kParkMaxLimbs && (park_mode > 0 || (park_mode < 0 && npx >= 2 * grid * kBlock));
         if (park) {
             const size_t cap = (size_t)grid * kBlock;
             const size_t state_words = (size_t)(6 * pl->n32 + 9) * cap;
@@ -805,6 +812,7 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         }
         fn<<<(unsigned)grid, kBlock, ki.shared_bytes, st>>>(p);
         CUDA_OK(cudaGetLastError());
+        pl->kernels_launched += 1;
         if (park) {
             p.phase = 1;
             park_sort_kernel<<<1, 1024, 0, st>>>(p.park_count, p.park_buf + (size_t)(6 * pl->n32 + 7) * p.park_cap,
@@ -813,6 +821,7 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
             CUDA_OK(cudaGetLastError());
             fn<<<(unsigned)grid, kBlock, ki.shared_bytes, st>>>(p);
             CUDA_OK(cudaGetLastError());
+            pl->kernels_launched += 2;
         }
     }
     CUDA_OK(cudaEventRecord(pl->done_ev, st));
@@ -933,6 +942,7 @@ extern "C" int mdzcuda_plan_recolour(mdzcuda_plan* pl, void* cuda_stream)
         recolour_kernel<<<blocks, 128, 0, (cudaStream_t)cuda_stream>>>(pl->d_raw, pl->view.real_width,
                                                                       pl->view.aa_factor, pl->nbands, pl->colour);
         CUDA_OK(cudaGetLastError());
+        pl->kernels_launched += 1;
     }
     CUDA_OK(cudaEventRecord(pl->done_ev, (cudaStream_t)cuda_stream));
     return 1;

@@ -177,6 +177,10 @@ class Plan:
         self._chk(_l.lib.mdzcuda_plan_fetch_rgb(self.h, out.ctypes.data_as(C.c_void_p)), "plan_fetch_rgb")
         return out
 
+    def kernels_launched(self):
+        """Kernels this plan has launched so far (3 per render with tail compaction, else 1)."""
+        return int(_l.lib.mdzcuda_plan_kernels_launched(self.h))
+
     def kernel_info(self):
         ki = _l.KernelInfo()
         self._chk(_l.lib.mdzcuda_plan_kernel_info(self.h, C.byref(ki)), "plan_kernel_info")
