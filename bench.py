@@ -317,22 +317,25 @@ def main():
         ki = plan.kernel_info()
         # per-launch figures of this kernel from the committed ncu capture (profiles/): DRAM
         # traffic and which pipe binds.  Static facts of the build, not measured in this run.
-        ncu = {}
+        ncu, ncu1 = {}, {}
         try:
             with open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")) as f:
-                ncu = json.load(f).get("ld64_cfg2", {})
+                both = json.load(f)
+            ncu = both.get("ld64_cfg2_phase0", {})       # phase 0: ~80 % of a render (profiles/r1_launches.csv)
+            ncu1 = both.get("ld64_cfg2_phase1", {})      # phase 1: the parked pixels (tail compaction)
         except (OSError, ValueError):
             pass
 
-        def ncu_num(key):
+        def ncu_num(key, src=None):
             try:
-                v, unit = ncu[key].split()[:2]
+                v, unit = (ncu if src is None else src)[key].split()[:2]
                 return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
             except (KeyError, ValueError, IndexError):
                 return None
         dram = None
-        if ncu_num("dram__bytes_read.sum") is not None and ncu_num("dram__bytes_write.sum") is not None:
-            dram = ncu_num("dram__bytes_read.sum") + ncu_num("dram__bytes_write.sum")
+        parts = [ncu_num(k, src) for src in (ncu, ncu1) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")]
+        if all(x is not None for x in parts):
+            dram = sum(parts)
         peak = mdz_b200.imad_peak(local, 200)                  # IMAD.WIDE.U32.X chains: 32x32->64 MAC/s
         peak32 = mdz_b200.imad_peak(local, 200, wide=False)    # 32-bit IMAD issue rate
         macs = macs_per_iteration(ki["limbs"] - 2 if view.mode == 2 else ki["limbs"])     # GMP mode multiplies the top P 64-bit limbs: N = 2P words
@@ -365,14 +368,16 @@ def main():
             "roofline": {"bound": "imad", "achieved": kernel_rate * macs / 1e12, "peak": peak / 1e12,
                          "unit": "T 32x32->64 MAC/s", "frac": kernel_rate * macs / peak,
                          "traffic": dram,
-                         "traffic_note": "dram__bytes_read+write of one launch (ncu --set full, profiles/r1_ncu_summary.json: ld64_cfg2); "
-                                         "the 8.3 MB of results stay in L2 until after the kernel",
+                         "traffic_note": "dram__bytes_read+write of one render = both launches of the escape kernel (ncu --set full, "
+                                         "profiles/r1_ncu_summary.json: ld64_cfg2_phase0 + ld64_cfg2_phase1): 0.18 MB in phase 0, 9.2 MB in "
+                                         "phase 1 reading the parked states back; the 8.3 MB of results stay in L2 until after the kernel",
                          "binding_pipe": {"pipe": "alu", "busy_pct": ncu_num("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
                                           "fma_pct": ncu_num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
                                           "fmaheavy_cycles_pct": ncu_num("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
                                           "fp64_pct": ncu_num("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
                                           "issue_active_pct": ncu_num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                                          "source": "ncu capture of this kernel on this workload (profiles/r1_ncu_summary.json: ld64_cfg2)",
+                                          "source": "ncu capture of this kernel on this workload (profiles/r1_ncu_summary.json: ld64_cfg2_phase0, "
+                                                    "the launch that is ~80 % of a render)",
                                           "why": "at 64 bits an iteration is 12 IMAD.WIDE against ~170 shift/compare/select/add "
                                                  "instructions of alignment, normalisation and rounding: the ALU pipe binds, not the multiplier"},
                          "peak_imad32": peak32 / 1e12,
