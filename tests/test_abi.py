@@ -50,3 +50,13 @@ def test_bad_arguments_are_rejected():
     v.depth = 0
     with pytest.raises(mdz_b200.MdzCudaError):
         mdz_b200.Plan(v)
+
+
+def test_null_plan_is_an_error_not_a_crash():
+    """Every plan entry point checks its handle: 0 (or -1 for the launch counter) and an
+    error text, as the reference's pool returns 0 on failure (src/render_threads.c:103-183)."""
+    from mdz_b200 import _native
+    lib = _native.lib
+    assert lib.mdzcuda_plan_kernels_launched(None) == -1
+    assert lib.mdzcuda_plan_set_parking(None, 1) == 0
+    assert b"null plan" in lib.mdzcuda_last_error()
