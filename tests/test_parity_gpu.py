@@ -221,6 +221,22 @@ def test_tail_compaction_changes_nothing(ref_lib, name, mk):
     assert np.array_equal(out, want)
 
 
+def test_tail_compaction_is_reported_and_limited_to_four_limbs():
+    """mdzcuda_plan_kernels_launched (bench.py's gpu_launches): a parked render is three launches
+    (phase 0, the ordering pass, phase 1), any other one.  Parking is compiled into the kernels of
+    up to four limbs only (escape_params.cuh kParkMaxLimbs); asking for it on a wider one is a no-op."""
+    for kw, park, want in ((dict(mode="ld"), 1, 3), (dict(mode="ld"), 0, 1),
+                           (dict(precision=128), 1, 3), (dict(precision=320), 1, 1)):
+        p = mdz_b200.Plan(make_view("-0.7", "0.1", "2.5", 96, 72, depth=300, **kw), 0)
+        p.set_parking(park)
+        assert p.kernels_launched() == 0
+        p.run()
+        assert p.kernels_launched() == want, (kw, park, p.kernels_launched())
+        p.run()
+        assert p.kernels_launched() == 2 * want
+        p.close()
+
+
 LEVEL2_VIEWS = [
     # long double mode, pixels on which the plain fast iteration declines for ever (DESIGN.md 4.3): the
     # column x = 0 and the row y = 0 (zero operands), rows next to the real axis (100-bit gaps), fixed
