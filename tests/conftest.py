@@ -19,6 +19,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A stuck test (a rendezvous that never completes, a pool that never signals) fails after ten
+    minutes instead of holding the whole run; needs pytest-timeout, a no-op without it."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(600))
+
+
 @pytest.fixture(scope="session")
 def emu_lib():
     """Host build of the device arithmetic headers (tests/host_emu): test-only."""

@@ -57,7 +57,11 @@ def test_gloo_world2_aggregate(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     env = dict(os.environ, MDZ_ROOT=ROOT)
+    import socket
+    with socket.socket() as sk:                      # a free rendezvous port: a fixed one may sit in TIME_WAIT
+        sk.bind(("127.0.0.1", 0))
+        port = str(sk.getsockname()[1])
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", port, str(script)],
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
