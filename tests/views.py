@@ -78,6 +78,23 @@ def config4(w=3840, h=2160, depth=100000, mode="gmp", precision=512):
     return make_view(DEEP120[0], DEEP120[1], "1e-120", w, h, mode=mode, precision=precision, depth=depth)
 
 
+# The same configuration on a view that holds a minibrot, as SURVEY 8(d) config 4 asks ("a minibrot
+# nucleus refined by Newton iteration ... so that part of the frame reaches maxiter (imbalanced load)"):
+# the period-707 nucleus 2e-61 away from the Misiurewicz point M(7,2) = -1.02004618 + 0.36748404i,
+# size 8.80e-122 (tests/golden/make_minibrot_center.py).  In a 1e-120 wide 16:9 frame the copy of the
+# set covers ~2 % of the pixels (they run to depth); the rest escapes after a few thousand iterations.
+# The centre puts the copy's middle (w = -0.5) at 40 % of the frame height.
+MINIBROT120 = ("-1.020046182259385217091865714835682856485530230077341008574363862552092767130751929513454984842547245021348825939975602029089382380660505102952920023722220432497713672616646017",
+               "0.3674840351832474379034844057678939574299590406994822242761426141816237076291546180151431726933838064685031011319634748791372673372535570498321917665285018130137968923407166453")
+MINIBROT120_NUCLEUS = ("-1.020046182259385217091865714835682856485530230077341008574363862552092767130751929513454984842547245021348825939975602029114599645677072089656815758406526854037775728211996565",
+                       "0.3674840351832474379034844057678939574299590406994822242761426141816237076291546180151431726933838064685031011319634748792295760419129867435812162956210919108393798335111629735")
+MINIBROT120_PERIOD = 707
+
+
+def config4m(w=3840, h=2160, depth=100000, mode="mpfr", precision=512):
+    return make_view(MINIBROT120[0], MINIBROT120[1], "1e-120", w, h, mode=mode, precision=precision, depth=depth)
+
+
 # BASELINE configs[4]: Burning Ship / generalized Celtic, 7680x4320 with 3x3 anti-aliasing
 def config5(fractal, w=7680, h=4320, aa=3, depth=1000, mode="ld", precision=64):
     cy = "-0.5" if fractal == BURNING_SHIP else "0.0"
