@@ -1,18 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- pixel-iterations/s of the escape-time path on B200.
 
-One "step" is one complete render of the workload view (reset queue + the
-persistent escape-time kernel).  At N=1 the workload is BASELINE.json
-configs[1]: the full Mandelbrot set, 1920x1080, MDZ's hardware-precision mode
-(x87 long double == 64-bit significand, SURVEY finding 1), depth 10000.  With N
-ranks (torchrun, one process per GPU) the same image is split into interleaved
-line bands, one plan per rank, no data-path collective ("strong" scaling).
+Default workload, the same at every N: the north star's target -- ONE 3840x2160 image of a
+1e-120 wide view at 512-bit MPFR precision, depth 100000, centred next to a minibrot so that
+2 % of the pixels run to depth (BASELINE configs[3] geometry, tests/views.py config4m).  One
+"step" is one complete render of it.  With N ranks (torchrun, one process per GPU) the image
+is split into interleaved line bands, one plan per rank, no data-path collective: strong
+scaling.  Untimed, inside the same run: every rank checks sampled lines of its share against
+the reference's own line driver, rank 0 renders the image once more through the library's own
+multi-device call (mdzcuda_render over all N devices from one process), and at N = 1 the other
+precisions of the metric are measured (`per_precision`, BASELINE configs[1] at full size among
+them with its own end-to-end figure).
 
-Prints ONE JSON line (rank 0).  `--impl reference` instead times the unmodified
-reference's own pthread pool (oracle/_ref/libmdzref.so) on the host cores.
+Prints ONE JSON line (rank 0).  `--impl reference` instead times the unmodified reference's own
+pthread pool (oracle/_ref/libmdzref.so) on the host cores, on a bounded sample of the same view.
 """
 import argparse
-import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -26,6 +30,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "pixel_iterations_per_sec"
 UNIT = "pixel-iterations/s"
+PROFILE_SUMMARY = os.path.join(ROOT, "profiles", "r2_ncu_summary.json")
 
 
 def macs_per_iteration(n_limbs):
@@ -33,33 +38,54 @@ def macs_per_iteration(n_limbs):
     return 2 * n_limbs * n_limbs + n_limbs
 
 
-def workload_cfg4(mode="mpfr"):
-    """BASELINE configs[3] / the north star's target: a 1e-120 wide view at 512 bits, 3840x2160,
-    depth 100000 (tests/views.py config4; every pixel escapes after ~12 800 iterations), in MPFR
-    mode (the north star's "512-bit MPFR-equivalent") or GMP mpf mode (as configs[3] names it).
-    One image split across the ranks by interleaved bands: strong scaling."""
-    from views import config4
-    return config4(3840, 2160, 100000, mode=mode, precision=512)
-
-
-def workload_view(world=1, scaling="weak"):
-    """BASELINE configs[1] at N=1.  With N ranks the path shards by line bands
-    (no collective), so by default the benchmark is weak-scaled: the same view at
-    N times the pixels (1920x1080 per GPU: 2716x1528 on 2, 3840x2160 on 4,
-    5432x3056 on 8), each rank rendering bands r, r+N, ...  `--scaling strong`
-    keeps the 1920x1080 image and splits it instead."""
-    from views import config2
-    if world == 1 or scaling == "strong":
-        return config2(1920, 1080, 10000)
-    f = world ** 0.5
-    w = int(round(1920 * f / 8.0)) * 8
-    h = int(round(1080 * f / 8.0)) * 8
-    return config2(w, h, 10000)
+# name -> (view factory, text, dtype text, scaling)
+def workload(name, world=1, scaling="strong"):
+    from views import config2, config4, config4m
+    if name == "target":
+        return (config4m(3840, 2160, 100000, mode="mpfr", precision=512),
+                "north-star target / BASELINE configs[3] geometry: 1e-120 wide view next to the period-707 minibrot at "
+                "M(7,2), 3840x2160, MPFR 512 bits, depth 100000, 2 % of the pixels run to depth",
+                "16 x u32 significand + i32 exponent (soft-float == MPFR at 512 bits, round to nearest even)", "strong")
+    if name == "targetgmp":
+        return (config4m(3840, 2160, 100000, mode="gmp", precision=512),
+                "BASELINE configs[3]: 1e-120 wide view next to the period-707 minibrot at M(7,2), 3840x2160, GMP mpf 512 bits, "
+                "depth 100000, 2 % of the pixels run to depth",
+                "20 x u32 words (9 + 1 64-bit limbs) + limb exponent (soft-float == GMP 6.3 mpf at 512 bits, truncating)", "strong")
+    if name == "cfg4":
+        return (config4(3840, 2160, 100000, mode="mpfr", precision=512),
+                "round 1's target view: 1e-120 wide on the Misiurewicz point M(23,2), 3840x2160, MPFR 512 bits, depth 100000, "
+                "every pixel escapes after ~12 800 iterations",
+                "16 x u32 significand + i32 exponent (soft-float == MPFR at 512 bits, round to nearest even)", "strong")
+    if name == "cfg2":
+        if world == 1 or scaling == "strong":
+            v = config2(1920, 1080, 10000)
+        else:                                   # weak: N x the pixels of the same view
+            f = world ** 0.5
+            v = config2(int(round(1920 * f / 8.0)) * 8, int(round(1080 * f / 8.0)) * 8, 10000)
+        return (v, "BASELINE configs[1]: full M-set cx=-0.5 cy=0 size=4, %dx%d, long double mode, depth 10000"
+                % (v.real_width, v.real_height),
+                "u64 significand + i32 exponent (soft-float == x87 long double, round to nearest even)",
+                "strong" if world == 1 else scaling)
+    raise SystemExit("unknown workload " + name)
 
 
 def iterations_of(raw, depth):
     import numpy as np
     return int(np.where(raw > 0, raw, depth).astype(np.int64).sum())
+
+
+def rank_lines(user_height, aa, rank, world):
+    """real lines of rank r's bands (r, r + world, ...): the partition mdzcuda_plan_create(first=r, stride=world) renders"""
+    return [l for b in range(rank, user_height, world) for l in range(b * aa, (b + 1) * aa)]
+
+
+def sample_of(lines, count):
+    """`count` of the given lines, evenly spread, first and last included"""
+    if count >= len(lines):
+        return list(lines)
+    if count <= 1:
+        return [lines[len(lines) // 2]]
+    return sorted(set(lines[int(round(k * (len(lines) - 1) / (count - 1)))] for k in range(count)))
 
 
 class ClockSampler:
@@ -116,29 +142,50 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ---------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------
+REF_SAMPLE = (192, 108)      # the bounded sample of the target view: the same rect at 1/400 of the pixels
+
+
+def reference_sample_view(name):
+    """The workload's own view -- same rect, precision, depth, mode -- at a resolution the host cores finish in
+    seconds.  (The whole 3840x2160 frame is ~65 G pixel-iterations: a quarter of an hour on 16 cores.)"""
+    from views import config2, config4, config4m
+    w, h = REF_SAMPLE
+    if name == "target":
+        return config4m(w, h, 100000, mode="mpfr", precision=512), "the same view at %dx%d (1/400 of the pixels)" % (w, h)
+    if name == "targetgmp":
+        return config4m(w, h, 100000, mode="gmp", precision=512), "the same view at %dx%d (1/400 of the pixels)" % (w, h)
+    if name == "cfg4":
+        return config4(w, h, 100000, mode="mpfr", precision=512), "the same view at %dx%d (1/400 of the pixels)" % (w, h)
+    return config2(1920, 1080, 10000), "the complete 1920x1080 frame"
+
+
 def run_reference(args, emit):
-    """Reference arm: the unmodified reference pool on the host cores."""
+    """Reference arm: the unmodified reference pool on the host cores (rank 0 only).  Maps nothing of the
+    product: mdz_b200 is imported for its host-side view builder only and loads libmdzcuda lazily."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import refpath
-    from views import config2
     lib = refpath.load()
     cores = os.cpu_count() or 1
-    # bounded sample: the same view at half resolution each way (same set, 1/4 of the pixels)
-    view = config2(960, 540, 10000)
+    view, sample_txt = reference_sample_view(args.workload)
+    full, text, dtype, _ = workload(args.workload, 1, "strong")
     kind = "reference"
     if lib is None:
         import portpath
         kind = "port"
+
+    def one(v):
+        t0 = time.perf_counter()
+        raw = refpath.ref_render(lib, v, cores)[0] if lib is not None else portpath.port_render(v, cores)
+        return time.perf_counter() - t0, raw
+
     times, iters = [], 0
     for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        if lib is not None:
-            raw, _ = refpath.ref_render(lib, view, cores)
-        else:
-            raw = portpath.port_render(view, cores)
-        dt = time.perf_counter() - t0
+        dt, raw = one(view)
         if i >= args.warmup:
             times.append(dt)
             iters = iterations_of(raw, view.depth)
@@ -148,38 +195,71 @@ def run_reference(args, emit):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "x87 long double (64-bit significand)",
-        "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: full M-set, long double, depth 10000 "
-                               "(sample rendered at 960x540)"},
+        "scaling": "strong", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": text, "same_config": True,
+                   "sample": "%s, %d pixel-iterations per step" % (sample_txt, iters)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": "same view at 960x540 (1/4 of the pixels), %d pixel-iterations per step, "
-                                   "reference pthread pool with -t %d" % (iters, cores)},
+                         "sample": "%s, %d pixel-iterations per step, reference pthread pool with -t %d"
+                                   % (sample_txt, iters, cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if args.workload != "cfg2" and not args.no_side:
+        # the hardware-precision configuration, complete (BASELINE configs[1]): affordable on host cores
+        from views import config2
+        v2 = config2(1920, 1080, 10000)
+        best = None
+        for _ in range(3):
+            dt, raw = one(v2)
+            best = dt if best is None or dt < best else best
+        line["per_precision"] = {"ld64_cfg2": {"value": iterations_of(raw, v2.depth) / best, "unit": UNIT, "ms": best * 1e3,
+                                               "view": "1920x1080 complete", "cores": cores}}
     emit(line)
 
 
-def side_precisions(torch, device):
-    """Kernel-only it/s at the other precisions of the metric, on bounded views."""
-    import mdz_b200
-    from views import make_view, SEAHORSE, deep_embedded_julia
-    out = {}
-    cases = [
-        ("mpfr128", make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", 1920, 1080, precision=128, depth=10000)),
-        ("mpfr320", deep_embedded_julia(960, 540)),
-        ("mpfr512", make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", 960, 540, precision=512, depth=10000)),
-        ("gmp512", make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", 960, 540, mode="gmp", precision=512, depth=10000)),
-    ]
-    peak = mdz_b200.imad_peak(device, 100)
-    peak32 = mdz_b200.imad_peak(device, 100, wide=False)
-    for name, view in cases:
-        plan = mdz_b200.Plan(view, device)
-        st = torch.cuda.current_stream().cuda_stream
-        plan.launch(st); plan.wait()                    # warm-up
+# ---------------------------------------------------------------------------
+# GPU arm, side measurements (N = 1 only)
+# ---------------------------------------------------------------------------
+def time_plan(torch, plan, repeats=1):
+    st = torch.cuda.current_stream().cuda_stream
+    plan.launch(st); plan.wait()                        # warm-up
+    best = None
+    for _ in range(repeats):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); plan.launch(st); e1.record(); e1.synchronize()
         ms = e0.elapsed_time(e1)
+        best = ms if best is None or ms < best else best
+    return best
+
+
+def side_precisions(torch, device, peak, peak32, skip=()):
+    """Kernel-only it/s at the other precisions of the metric; BASELINE configs[1] (long double, complete
+    1920x1080) also end to end through the C ABI with host buffers."""
+    import numpy as np
+    import mdz_b200
+    from views import make_view, SEAHORSE, deep_embedded_julia, config2
+    out = {}
+    sea = lambda w, h, **kw: make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", w, h, depth=10000, **kw)     # noqa: E731
+    cases = [
+        ("ld64_cfg2", config2(1920, 1080, 10000)),
+        ("mpfr80", sea(1920, 1080, precision=80)),
+        ("mpfr128", sea(1920, 1080, precision=128)),
+        ("mpfr320", deep_embedded_julia(1920, 1080)),
+        ("mpfr512", sea(960, 540, precision=512)),
+        ("gmp512", sea(960, 540, mode="gmp", precision=512)),
+        ("mpfr1024", sea(480, 270, precision=1024)),
+        ("mpfr2048", sea(240, 135, precision=2048)),
+        ("mpfr4096", sea(160, 90, precision=4096)),
+    ]
+    stream = torch.cuda.current_stream().cuda_stream
+    for name, view in cases:
+        if name in skip:
+            continue
+        try:
+            plan = mdz_b200.Plan(view, device)
+        except mdz_b200.MdzCudaError as ex:
+            out[name] = {"value": None, "unit": UNIT, "error": str(ex)}
+            continue
+        ms = time_plan(torch, plan, 3 if name == "ld64_cfg2" else 1)
         iters = iterations_of(plan.fetch(), view.depth)
         ki = plan.kernel_info()
         rate = iters / (ms * 1e-3)
@@ -188,12 +268,61 @@ def side_precisions(torch, device):
         out[name] = {"value": rate, "unit": UNIT, "ms": ms, "pixel_iterations": iters,
                      "view": "%dx%d" % (view.real_width, view.real_height),
                      "limbs": ki["limbs"], "mac_limbs": n_mac, "macs_per_iteration": macs_per_iteration(n_mac),
+                     "lanes_per_pixel": ki.get("lanes_per_pixel", 1),
                      "regs": ki["regs_per_thread"], "spill_bytes": ki["local_bytes"],
                      "blocks_per_sm": ki["blocks_per_sm"],
                      "imad_frac": rate * macs_per_iteration(n_mac) / peak,
                      "frac_of_imad32_issue": rate * macs_per_iteration(n_mac) / peak32}
         plan.close()
+        if name == "ld64_cfg2":
+            res = np.empty((view.real_height, view.real_width), dtype=np.int32)
+            for _ in range(2):
+                p2 = mdz_b200.Plan(view, device); p2.run(res, stream); p2.close()
+            t0 = time.perf_counter()
+            n = 10
+            for _ in range(n):
+                p2 = mdz_b200.Plan(view, device); p2.run(res, stream); p2.close()
+            dt = (time.perf_counter() - t0) / n
+            out[name]["e2e"] = {"value": iters / dt, "unit": UNIT, "ms": dt * 1e3, "steps": n,
+                                "h2d_bytes_per_step": 16 * (view.real_width + view.real_height + 2),
+                                "d2h_bytes_per_step": int(res.nbytes)}
+            # NOT the metric: the same render with the exact periodicity check on (what the rth_* drop-in runs)
+            ms2 = []
+            for _ in range(4):
+                ta = time.perf_counter()
+                p3 = mdz_b200.Plan(view, device)
+                p3.set_cycle_detection(True)
+                got = p3.run(stream=stream)
+                p3.close()
+                ms2.append((time.perf_counter() - ta) * 1e3)
+            out[name]["cycle_detection"] = {"e2e_ms": min(ms2[1:]), "identical_raw_data": bool(np.array_equal(got, res)),
+                                            "note": "opt-in exact periodicity check; no it/s figure is derived from it"}
     return out
+
+
+def static_profile(kernel_key):
+    """ncu figures of a kernel from the committed capture (profiles/): a static fact of the build, NOT measured in
+    this run -- the JSON says so."""
+    try:
+        with open(PROFILE_SUMMARY) as f:
+            both = json.load(f)
+    except (OSError, ValueError):
+        return None, None
+    ent = both.get(kernel_key)
+    if not ent:
+        return None, both.get("_meta")
+    return ent, both.get("_meta")
+
+
+def ncu_num(ent, key):
+    try:
+        v, unit = str(ent[key]).split()[:2]
+        return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+    except (KeyError, ValueError, IndexError, TypeError):
+        try:
+            return float(ent[key])
+        except (KeyError, ValueError, TypeError):
+            return None
 
 
 def main():
@@ -207,15 +336,16 @@ def main():
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-side", action="store_true", help="skip the per-precision side measurements")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4", "cfg4gmp"],
-                    help="cfg2 (default, the bench contract's workload): BASELINE configs[1]; cfg4: the north star's "
-                         "target view, 3840x2160 at 512-bit MPFR, depth 100000, one image split over the ranks")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N>1: weak = same view at N x the pixels (default), strong = split the 1920x1080 image")
+    ap.add_argument("--no-check", action="store_true", help="skip the untimed comparison with the reference's line driver")
+    ap.add_argument("--workload", default="target", choices=["target", "targetgmp", "cfg4", "cfg2"],
+                    help="target (default): the north star's 3840x2160 MPFR-512 image, split over the ranks; targetgmp: the same "
+                         "in GMP mpf mode; cfg4: round 1's minibrot-free view; cfg2: BASELINE configs[1] (long double)")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="cfg2 only, N>1: strong = split the 1920x1080 image (default), weak = N x the pixels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
 
@@ -234,24 +364,28 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")      # barriers that do not put a spinning kernel on the GPUs
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    cfg4 = args.workload in ("cfg4", "cfg4gmp")
-    gmp4 = args.workload == "cfg4gmp"
-    if cfg4:
-        args.scaling = "strong"
-        args.no_side = True
-    view = workload_cfg4("gmp" if gmp4 else "mpfr") if cfg4 else workload_view(world, args.scaling)
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
+    view, wl_text, dtype_text, scaling = workload(args.workload, world, args.scaling)
+    deep = args.workload != "cfg2"
     plan = mdz_b200.Plan(view, local, band_first=rank, band_stride=world)
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
+    # ---- device-timed: W warm-up renders, then exactly K, barrier + synchronize on both sides ----
     for _ in range(args.warmup):
         flush.zero_()
         plan.launch(stream)
@@ -276,25 +410,25 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     raw = plan.fetch()
-    my_lines = raw[[l for b in range(rank, view.user_height, world)
-                    for l in range(b * view.aa_factor, (b + 1) * view.aa_factor)]]
+    mine = rank_lines(view.user_height, view.aa_factor, rank, world)
+    my_lines = raw[mine]
     my_iters = iterations_of(my_lines, view.depth)
     t = torch.tensor([ms_total, kernel_ms], dtype=torch.float64, device="cuda")
-    it = torch.tensor([my_iters, my_launches], dtype=torch.int64, device="cuda")
+    it = torch.tensor([my_iters, my_launches, int(mdz_b200.fallback_lines())], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(it, op=dist.ReduceOp.SUM)
     ms_total, kernel_ms = float(t[0]), float(t[1])
-    total_iters = int(it[0])
-    total_launches = int(it[1])
+    total_iters, total_launches, fallback_lines = int(it[0]), int(it[1]), int(it[2])
     value = total_iters * args.steps / (ms_total * 1e-3)
 
     # ---- end-to-end through the public call: host view in, host raw_data out ----
-    xs_bytes = (plan.kernel_info()["limbs"] + 2) * 4 * (view.real_width + plan.local_lines() + 2)
-    e2e_steps = max(1, min(args.steps, 2 if cfg4 else 20))
+    ki = plan.kernel_info()
+    xs_bytes = (ki["limbs"] + 2) * 4 * (view.real_width + plan.local_lines() + 2)
+    e2e_steps = max(1, min(args.steps, 2 if deep else 20))
     out = np.empty((view.real_height, view.real_width), dtype=np.int32)   # the caller's raw_data (pageable, as MDZ's malloc)
     out.fill(-1)
-    for _ in range(1 if cfg4 else 2):                                           # untimed: pool warm, pages touched
+    for _ in range(1 if deep else 2):                                           # untimed: pool warm, pages touched
         p2 = mdz_b200.Plan(view, local, band_first=rank, band_stride=world); p2.run(out, stream); p2.close()
     barrier()
     e2e_ms = []
@@ -311,141 +445,129 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = total_iters * e2e_steps / float(te[0])
-    assert np.array_equal(out[rank * view.aa_factor], raw[rank * view.aa_factor])
+    e2e_same = bool(np.array_equal(out[mine], my_lines))
+
+    # ---- untimed: every rank checks sampled lines of its share against the reference's own line driver ----
+    cores = os.cpu_count() or 1
+    check = {"identical": None, "lines": 0, "seconds": 0.0}
+    ref_lib = None
+    if not args.no_check:
+        try:
+            import refpath
+            ref_lib = refpath.load()
+        except Exception:
+            ref_lib = None
+    if ref_lib is not None:
+        threads = max(1, cores // world)
+        lines = sample_of(mine, threads if deep else min(len(mine), 8 * threads))
+        tc = time.perf_counter()
+        want = refpath.ref_render_lines(ref_lib, view, lines, threads)
+        check = {"identical": bool(np.array_equal(want, raw[lines])), "lines": len(lines),
+                 "seconds": time.perf_counter() - tc}
+    flags = [check]
+    digest = hashlib.sha256(np.ascontiguousarray(my_lines).tobytes()).hexdigest()
+    digests = [digest]
+    if world > 1:
+        flags = [None] * world
+        digests = [None] * world
+        dist.all_gather_object(flags, check, group=cpu_group)
+        dist.all_gather_object(digests, digest, group=cpu_group)
+    host_barrier()
+
+    # ---- untimed: the library's own multi-device call, from ONE process over all N devices ----
+    single = None
+    if rank == 0:
+        devs = tuple(range(world))
+        try:
+            if world > 1:
+                mdz_b200.render(view, devs)                       # contexts, pools, module load on the other devices
+            ts = time.perf_counter()
+            whole = mdz_b200.render(view, devs)
+            dt = time.perf_counter() - ts
+            same = [hashlib.sha256(np.ascontiguousarray(whole[rank_lines(view.user_height, view.aa_factor, r, world)]).tobytes()).hexdigest()
+                    == digests[r] for r in range(world)]
+            single = {"call": "mdzcuda_render(view, raw_host, ndev=%d)" % world, "devices": list(devs),
+                      "e2e_value": iterations_of(whole, view.depth) / dt, "unit": UNIT, "ms": dt * 1e3,
+                      "identical_to_per_rank_result": bool(all(same)),
+                      "fallback_lines": int(mdz_b200.fallback_lines())}
+        except mdz_b200.MdzCudaError as ex:
+            single = {"call": "mdzcuda_render(view, raw_host, ndev=%d)" % world, "error": str(ex)}
+        torch.cuda.set_device(local)
+    host_barrier()
 
     if rank == 0:
-        ki = plan.kernel_info()
-        # per-launch figures of this kernel from the committed ncu capture (profiles/): DRAM
-        # traffic and which pipe binds.  Static facts of the build, not measured in this run.
-        ncu, ncu1 = {}, {}
-        try:
-            with open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")) as f:
-                both = json.load(f)
-            ncu = both.get("ld64_cfg2_phase0", {})       # phase 0: ~80 % of a render (profiles/r1_launches.csv)
-            ncu1 = both.get("ld64_cfg2_phase1", {})      # phase 1: the parked pixels (tail compaction)
-        except (OSError, ValueError):
-            pass
-
-        def ncu_num(key, src=None):
-            try:
-                v, unit = (ncu if src is None else src)[key].split()[:2]
-                return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
-            except (KeyError, ValueError, IndexError):
-                return None
-        dram = None
-        parts = [ncu_num(k, src) for src in (ncu, ncu1) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")]
-        if all(x is not None for x in parts):
-            dram = sum(parts)
         peak = mdz_b200.imad_peak(local, 200)                  # IMAD.WIDE.U32.X chains: 32x32->64 MAC/s
         peak32 = mdz_b200.imad_peak(local, 200, wide=False)    # 32-bit IMAD issue rate
         macs = macs_per_iteration(ki["limbs"] - 2 if view.mode == 2 else ki["limbs"])     # GMP mode multiplies the top P 64-bit limbs: N = 2P words
         kernel_rate = (total_iters / world) / (kernel_ms * 1e-3)        # this GPU's kernel alone
+        kernel_key = {"target": "mpfr512_target", "targetgmp": "gmp512_target", "cfg4": "mpfr512_target", "cfg2": "ld64_cfg2_phase0"}[args.workload]
+        prof, meta = static_profile(kernel_key)
+        dram = None
+        if prof:
+            parts = [ncu_num(prof, k) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")]
+            dram = sum(parts) if all(x is not None for x in parts) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": args.scaling if (world > 1 or cfg4) else "weak", "vs_baseline": None,
-            "dtype": ("20 x u32 words (9 + 1 64-bit limbs) + limb exponent (soft-float == GMP 6.3 mpf at 512 bits, truncating)" if gmp4 else
-                      "16 x u32 significand + i32 exponent (soft-float == MPFR at 512 bits, round to nearest even)" if cfg4 else
-                      "u64 significand + i32 exponent (soft-float == x87 long double, round to nearest even)"),
-            "data": "synthetic",
-            "config": {"workload": ("BASELINE configs[3] / north-star target: 1e-120 wide view on M(23,2), 3840x2160, %s 512 bits, "
-                                    "depth 100000, one image split over %d GPU(s) (strong scaling)" % ("GMP mpf" if gmp4 else "MPFR", world)) if cfg4 else
-                                   "BASELINE configs[1]: full M-set cx=-0.5 cy=0 size=4, %dx%d, "
-                                   "long double mode, depth 10000%s" % (
-                                       view.real_width, view.real_height,
-                                       "" if world == 1 else (" (weak scaling: 1920x1080 pixels per GPU)" if args.scaling == "weak"
-                                                               else " (strong scaling: one 1920x1080 image split)")),
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": dtype_text, "data": "synthetic",
+            "config": {"workload": wl_text + ("; one image split over %d GPU(s)" % world),
                        "pixel_iterations_per_step": total_iters,
                        "partition": "interleaved line bands, one plan per rank, no collective",
                        "l2": "256 MiB buffer rewritten between steps (inputs are KB-sized tables)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps,
                     "h2d_bytes_per_step": xs_bytes, "d2h_bytes_per_step": int(my_lines.nbytes),
-                    "ms_each": e2e_ms,
+                    "ms_each": e2e_ms, "identical_to_device_timed_result": e2e_same,
                     "includes": "mdzcuda_plan_create (host prologue with libmpfr/long double, H2D of the tables) + "
                                 "mdzcuda_plan_run (kernel, D2H of finished bands into pageable host raw_data) + destroy"},
             "gpu_launches": total_launches,
+            "fallback_lines": fallback_lines,
             "clocks": clocks,
+            "identical_to_reference_on_sample": (all(f["identical"] for f in flags) if all(f["identical"] is not None for f in flags) else None),
+            "reference_check": {"per_rank": flags,
+                                "how": "each rank: the reference's own line driver (oracle/_ref/libmdzref.so, ref_render_lines) on evenly "
+                                       "spread lines of its share of the full-size view, compared with the device-timed result; untimed"},
+            "single_process_ndev": single,
             "roofline": {"bound": "imad", "achieved": kernel_rate * macs / 1e12, "peak": peak / 1e12,
                          "unit": "T 32x32->64 MAC/s", "frac": kernel_rate * macs / peak,
+                         "peak_imad32": peak32 / 1e12, "frac_of_imad32_issue": kernel_rate * macs / peak32,
                          "traffic": dram,
-                         "traffic_note": "dram__bytes_read+write of one render = both launches of the escape kernel (ncu --set full, "
-                                         "profiles/r1_ncu_summary.json: ld64_cfg2_phase0 + ld64_cfg2_phase1): 0.18 MB in phase 0, 9.2 MB in "
-                                         "phase 1 reading the parked states back; the 8.3 MB of results stay in L2 until after the kernel",
-                         "binding_pipe": {"pipe": "alu", "busy_pct": ncu_num("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
-                                          "fma_pct": ncu_num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
-                                          "fmaheavy_cycles_pct": ncu_num("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
-                                          "fp64_pct": ncu_num("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
-                                          "issue_active_pct": ncu_num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                                          "source": "ncu capture of this kernel on this workload (profiles/r1_ncu_summary.json: ld64_cfg2_phase0, "
-                                                    "the launch that is ~80 % of a render)",
-                                          "why": "at 64 bits an iteration is 12 IMAD.WIDE against ~170 shift/compare/select/add "
-                                                 "instructions of alignment, normalisation and rounding: the ALU pipe binds, not the multiplier"},
-                         "peak_imad32": peak32 / 1e12,
-                         "frac_of_imad32_issue": kernel_rate * macs / peak32,
-                         "note": "integer-pipe roofline (SURVEY 8d), not hbm/tensor. achieved = it/s x W(N)=2N^2+N "
+                         "binding_pipe": None if not prof else {
+                             "static": True, "source": "profiles/r2_ncu_summary.json: " + kernel_key,
+                             "captured_at_rev": (meta or {}).get("rev"),
+                             "alu_pct": ncu_num(prof, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                             "fma_pct": ncu_num(prof, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                             "fmaheavy_cycles_pct": ncu_num(prof, "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+                             "fp64_pct": ncu_num(prof, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                             "issue_active_pct": ncu_num(prof, "smsp__issue_active.avg.pct_of_peak_sustained_active")},
+                         "note": "integer-pipe roofline (SURVEY 8d), not hbm/tensor. achieved = this GPU's it/s x W(N)=2N^2+N "
                                  "full-schoolbook MACs (N=%d limbs -> %d; the kernel forms only the high ~59%% of each "
                                  "product, DESIGN.md 2.1); peak = IMAD.WIDE.U32.X carry-chain microbenchmark measured in "
                                  "this run (MEASURED_PEAKS.json has no integer peak); peak_imad32 = 32-bit IMAD issue rate, "
-                                 "twice that; kernel avg %.3f ms per render by CUDA events (%d launch(es) per render: with tail "
-                                 "compaction the escape kernel runs twice around a one-block ordering pass); HBM traffic is 4 B per pixel out"
+                                 "twice that; kernel avg %.3f ms per render by CUDA events on the launching stream (%d launch(es) per render); "
+                                 "HBM traffic is 4 B per pixel out; traffic / binding_pipe are static figures of the committed ncu capture"
                                  % (ki["limbs"], macs, kernel_ms, total_launches // max(1, args.steps * world))},
             "kernel": ki,
         }
-        if cfg4:
-            # the committed ncu figures are the long double kernel's: for this workload say what binds from
-            # the 512-bit capture instead (profiles/r1_ncu_summary.json: mpfr512_seahorse_960x540)
-            line["roofline"]["traffic"] = None
-            line["roofline"].pop("traffic_note", None)
-            line["roofline"]["binding_pipe"] = {"pipe": "fmaheavy + alu", "source": "no ncu capture of the GMP kernel this round",
-                                                "why": "escape_gmpf_kernel<20>: 666 MACs per iteration in full-schoolbook terms"} if gmp4 else {
-                "pipe": "fmaheavy + alu (issue-limited)", "source": "profiles/r1_ncu_summary.json: mpfr512_seahorse_960x540",
-                "why": "escape_mpfr_kernel<16>: 1281 issue slots per iteration of which 311 IMAD.WIDE; fmaheavy 57 %, ALU 54 %, "
-                       "issue slots 51 % busy at 3 warps per scheduler (168 registers)"}
-        # CPU baseline: the unmodified reference pool on this box's cores, bounded sample
+        # CPU baseline: the unmodified reference pool on this box's cores, bounded sample of the same view
         try:
-            import refpath
-            from views import config2
-            lib = refpath.load()
-            cores = os.cpu_count() or 1
-            t0 = time.perf_counter()
-            if cfg4:
-                lines = [(2 * k + 1) * view.real_height // (2 * cores) for k in range(cores)]    # one line per thread
-                rraw = refpath.ref_render_lines(lib, view, lines, cores)
-                sample_txt = "%d evenly spaced lines of the same 3840x2160 view, the reference's own line driver" % len(lines)
-                sdepth = view.depth
-                same = bool(np.array_equal(rraw, raw[lines])) if world == 1 else None
-            else:
-                sample = config2(960, 540, 10000)
-                rraw, _ = refpath.ref_render(lib, sample, cores)
-                sample_txt = "same view at 960x540, unmodified reference pool"
-                sdepth = sample.depth
-                same = None
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": iterations_of(rraw, sdepth) / dt, "unit": UNIT,
+            if ref_lib is None:
+                raise RuntimeError("oracle/_ref/libmdzref.so not available")
+            sview, sample_txt = reference_sample_view(args.workload)
+            tb = time.perf_counter()
+            rraw, _ = refpath.ref_render(ref_lib, sview, cores)
+            dt = time.perf_counter() - tb
+            line["cpu_baseline"] = {"value": iterations_of(rraw, sview.depth) / dt, "unit": UNIT,
                                     "cores": cores, "kind": "reference",
-                                    "sample": "%s, -t %d, %.2f s" % (sample_txt, cores, dt)}
-            if same is not None:
-                line["cpu_baseline"]["identical_to_gpu_on_sample"] = same
+                                    "sample": "%s, unmodified reference pool, -t %d, %.2f s" % (sample_txt, cores, dt)}
         except Exception as ex:   # the reference .so is optional on the box
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)}
         if not args.no_side and world == 1:
-            line["per_precision"] = side_precisions(torch, local)
-            # NOT the metric: the same render with the exact periodicity check on (include/mdzcuda.h),
-            # i.e. what a user of the drop-in gets.  raw_data is identical; iterations performed are not
-            # the reference's count any more, so no it/s figure is derived from it.
-            ms = []
-            for _ in range(4):
-                ta = time.perf_counter()
-                p3 = mdz_b200.Plan(view, local)
-                p3.set_cycle_detection(True)
-                got = p3.run(stream=stream)
-                p3.close()
-                ms.append((time.perf_counter() - ta) * 1e3)
-            line["cycle_detection"] = {"e2e_ms": min(ms[1:]), "e2e_ms_full_iteration": min(e2e_ms),
-                                       "identical_raw_data": bool(np.array_equal(got, raw)),
-                                       "note": "opt-in exact periodicity check; value / e2e above are measured with it off"}
+            line["per_precision"] = side_precisions(torch, local, peak, peak32,
+                                                    skip=("ld64_cfg2",) if args.workload == "cfg2" else ())
         emit(line)
     plan.close()
+    host_barrier()
     if world > 1:
         dist.destroy_process_group()
 

@@ -31,6 +31,11 @@ extern "C" {
 #endif
 
 /* which reference line driver is being replaced */
+/* MODE_LD reproduces x87 extended precision: 64-bit significand, round to nearest even.  The exponent is
+ * an int32 here, so an orbit that squares itself below 2^-16382 (Julia, c = 0) keeps being squared where
+ * the x87 would go through denormals to zero; such a pixel never escapes in either arithmetic, so no
+ * iteration count depends on it (DESIGN.md "exponent range").  Coordinates beyond 2^+-16000 are rejected
+ * as zero / infinity by the prologue. */
 #define MDZCUDA_MODE_LD    0   /* fractal_calculate_line       src/fractal.c:29  (x87 long double)   */
 #define MDZCUDA_MODE_MPFR  1   /* fractal_mpfr_calculate_line  src/fractal.c:120 (MPFR, RNDN)        */
 #define MDZCUDA_MODE_GMP   2   /* fractal_gmp_calculate_line   src/fractal.c:260 (GMP mpf, truncate) */
@@ -65,6 +70,13 @@ typedef struct mdzcuda_view {
     /* img->u.julia.c_re / c_im, read only when family is julia (fractal.c:55-59,197-198,341-342) */
     const __mpfr_struct* julia_re;
     const __mpfr_struct* julia_im;
+    /* Optional, GMP mode + julia family only: the constant as mpf.  NULL (what the rth_* layer passes)
+     * reproduces the reference literally: julia_re / julia_im through the decimal text that
+     * mpfr_snprintf("%.Re") prints (src/my_mpfr_to_str.c:68, src/coords.c:13-18, src/fractal.c:341-342),
+     * which keeps ONE significant digit with MPFR >= 4.  A host that converts differently (the
+     * "%Re" build of the oracle, the Python harness with fixed_re) fills these instead. */
+    const __mpf_struct*  gjulia_re;
+    const __mpf_struct*  gjulia_im;
 } mdzcuda_view;
 
 typedef struct mdzcuda_plan mdzcuda_plan;
@@ -74,6 +86,23 @@ const char* mdzcuda_last_error(void);
 
 /* Number of CUDA devices visible; 0 (with an error text) if CUDA is unusable. */
 int mdzcuda_device_count(void);
+
+/*
+ * 1 when a GPU kernel is instantiated for the view's mode and precision, else 0 with the reason in
+ * mdzcuda_last_error().  MDZ's settings admit 80..99999999 bits (src/image_info.c:535); kernels exist
+ * for long double, MPFR 33..8192 bits and GMP mpf to 512 bits.  The rth_* layer renders everything else
+ * with the line callback the host installed (src/image_info.c:243-248), i.e. on the CPU, with one line
+ * on stderr -- see mdzcuda_fallback_lines.
+ */
+int mdzcuda_view_supported(const mdzcuda_view* view);
+
+/*
+ * Image lines (real lines) that the rth_* layer has rendered through the host's next_line callback
+ * instead of on the GPU since the library was loaded: unsupported precision / mode, no CUDA device, or
+ * a CUDA failure in mid-render.  0 means every line so far came from the CUDA kernels; the GPU parity
+ * tests and bench.py assert exactly that.  The plain entry points below never fall back: they fail.
+ */
+long mdzcuda_fallback_lines(void);
 
 /*
  * Build a render plan on one device: runs the O(W+H) host prologue (column
@@ -86,6 +115,21 @@ int mdzcuda_device_count(void);
  */
 mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* view, int device,
                                   int band_first, int band_stride);
+
+/*
+ * Band scheduler (several devices on one image; the reference's analogue is rth_next_line,
+ * src/render_threads.c:360-393, handing out one band at a time under a mutex).  A *fed* plan covers
+ * the whole image (band_first 0, band_stride 1) but renders only the bands the host feeds it, while
+ * its persistent kernel is running: mdzcuda_plan_feed appends `count` bands to the plan's queue and,
+ * with close != 0, tells the kernel that no more will come (it then ends once its queue is done).
+ * mdzcuda_plan_backlog is the number of pixels fed but not yet claimed by a lane, as of the last
+ * mdzcuda_plan_poll_bands.  mdzcuda_render drives these for ndev > 1; they are exported for hosts
+ * that run their own scheduler.  mdzcuda_plan_stream is the plan's own non-blocking stream.
+ */
+int       mdzcuda_plan_set_fed(mdzcuda_plan*, int on);
+int       mdzcuda_plan_feed(mdzcuda_plan*, const int* bands, int count, int close);
+long long mdzcuda_plan_backlog(mdzcuda_plan*);
+void*     mdzcuda_plan_stream(mdzcuda_plan*);
 
 /* Tunables (before launch): iterations between queue refills (0 = default; a
  * negative value -n means n with the speculative iteration body switched off,
@@ -200,9 +244,12 @@ void mdzcuda_plan_destroy(mdzcuda_plan*);
 void mdzcuda_trim(void);
 
 /*
- * One-call render: host view in, host raw_data out, over ndev devices
- * (devices == NULL means 0..ndev-1), bands interleaved across devices.
- * This is what the rth_* layer runs per render.  Returns 1 on success.
+ * One-call render: host view in, host raw_data out, over ndev devices (devices == NULL means
+ * 0..ndev-1).  With one device the image is one plan; with several, every device gets a fed plan and
+ * a host-side scheduler hands out chunks of bands on demand -- large chunks first, small ones at the
+ * end -- so that a device that is slower (busy with other work, or holding the deep part of the
+ * image) simply takes fewer (MDZCUDA_SCHED=static: fixed interleave instead, for A/B runs).  This is
+ * what the rth_* layer runs per render.  Returns 1 on success.
  */
 int mdzcuda_render(const mdzcuda_view* view, int32_t* raw_host,
                    int ndev, const int* devices);
@@ -218,6 +265,10 @@ int mdzcuda_render(const mdzcuda_view* view, int32_t* raw_host,
  */
 double mdzcuda_imad_peak(int device, int ms);
 double mdzcuda_imad32_peak(int device, int ms);
+
+/* Test hook: occupy `blocks` SMs of `device` for `ms` milliseconds with a kernel that leaves no room
+ * beside it (a device busy with someone else's work, for the band scheduler's tests).  Asynchronous. */
+int mdzcuda_debug_occupy(int device, int blocks, int ms);
 
 #ifdef __cplusplus
 }

@@ -7,4 +7,4 @@ Python binding used by the tests, bench.py and the GTK-free harness.
 from ._native import lib, last_error, MdzCudaError, LIB_PATH  # noqa: F401
 from .render import (ImageView, Plan, render, MODE_LD, MODE_MPFR, MODE_GMP,  # noqa: F401
                      FAMILY_MANDEL, FAMILY_JULIA, MANDELBROT, BURNING_SHIP,
-                     GENERALIZED_CELTIC, VARIANT, imad_peak, device_count)
+                     GENERALIZED_CELTIC, VARIANT, imad_peak, device_count, fallback_lines, view_supported)

@@ -29,6 +29,7 @@ class View(C.Structure):
         ("gxmin", C.POINTER(MpfStruct)), ("gymax", C.POINTER(MpfStruct)),
         ("gwidth", C.POINTER(MpfStruct)),
         ("julia_re", C.POINTER(MpfrStruct)), ("julia_im", C.POINTER(MpfrStruct)),
+        ("gjulia_re", C.POINTER(MpfStruct)), ("gjulia_im", C.POINTER(MpfStruct)),
     ]
 
 
@@ -48,6 +49,12 @@ class KernelInfo(C.Structure):
 SYMBOLS = {
     "mdzcuda_last_error": (C.c_char_p, []),
     "mdzcuda_device_count": (C.c_int, []),
+    "mdzcuda_view_supported": (C.c_int, [C.POINTER(View)]),
+    "mdzcuda_fallback_lines": (C.c_long, []),
+    "mdzcuda_plan_set_fed": (C.c_int, [C.c_void_p, C.c_int]),
+    "mdzcuda_plan_feed": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int]),
+    "mdzcuda_plan_backlog": (C.c_longlong, [C.c_void_p]),
+    "mdzcuda_plan_stream": (C.c_void_p, [C.c_void_p]),
     "mdzcuda_plan_create": (C.c_void_p, [C.POINTER(View), C.c_int, C.c_int, C.c_int]),
     "mdzcuda_plan_tune": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mdzcuda_plan_set_cycle_detection": (C.c_int, [C.c_void_p, C.c_int]),
@@ -73,6 +80,7 @@ SYMBOLS = {
     "mdzcuda_render": (C.c_int, [C.POINTER(View), C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "mdzcuda_imad_peak": (C.c_double, [C.c_int, C.c_int]),
     "mdzcuda_imad32_peak": (C.c_double, [C.c_int, C.c_int]),
+    "mdzcuda_debug_occupy": (C.c_int, [C.c_int, C.c_int, C.c_int]),
 }
 
 
@@ -91,7 +99,19 @@ def load():
     return lib
 
 
-lib = load()
+class _Lib:
+    """The library, mapped at the first call rather than at import: host-only users of this package
+    (the coords / .mdz / palette mirror, and bench.py's reference arm, which must not map any of the
+    product's code) never touch it.  A missing build still fails loudly, at the first use."""
+    _h = None
+
+    def __getattr__(self, name):
+        if _Lib._h is None:
+            _Lib._h = load()
+        return getattr(_Lib._h, name)
+
+
+lib = _Lib()
 
 
 def last_error():

@@ -49,6 +49,86 @@ __device__ __forceinline__ bool publish_bands(const EscapeParams& p, int finishe
     return true;
 }
 
+
+// ---------------------------------------------------------------------------
+// The pixel queue.
+//
+// Static plans: position q of the queue is pixel q of the plan's own lines (raster order).
+// Fed plans (p.order != nullptr; several devices sharing one image, mdzcuda.cu "band scheduler"):
+// the queue runs over *slots* of one band (aa lines) each, and the host fills the slots while the
+// kernel runs -- p.order[slot] is the band it put there, p.feed[0] the number of slots filled so
+// far, p.feed[1] == p.gen once no more will come.  A lane whose claim lies beyond the filled part
+// keeps it as a reservation (the index stays in `idx` with kReserved set) and looks again at the next
+// refill; after the close, reservations beyond the final limit are void.  The host writes order[],
+// then feed[0], then feed[1], in stream order; the device reads them in the opposite order.
+// ---------------------------------------------------------------------------
+constexpr unsigned kReserved = 0x80000000u;      // top bit of a lane's pixel index: it is a reservation (images hold < 2^31 pixels)
+
+__device__ __forceinline__ bool claim_pixels(const EscapeParams& p, unsigned lane, unsigned total, bool active,
+                                             unsigned& idx, bool& exhausted)
+{
+    bool start = false;
+    unsigned limit = total;
+    bool closed = true;
+    bool pending = false;
+    if (p.feed) {
+        unsigned f0 = 0, f1 = 0;
+        if (lane == 0) { f1 = p.feed[1]; __threadfence(); f0 = p.feed[0]; }
+        f0 = __shfl_sync(0xffffffffu, f0, 0);
+        f1 = __shfl_sync(0xffffffffu, f1, 0);
+        closed = f1 == p.gen;
+        limit = f0 * ((unsigned)p.width * (unsigned)p.aa);
+        pending = !active && (idx & kReserved) != 0u;
+        if (pending) {
+            const unsigned want = idx & ~kReserved;
+            if (want < limit) { idx = want; start = true; pending = false; }
+            else if (closed) { idx = 0u; pending = false; }
+        }
+    }
+    if (!exhausted) {
+        const unsigned need = __ballot_sync(0xffffffffu, !active && !pending && !start);
+        if (need) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(p.queue, (unsigned)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned end = base + (unsigned)__popc(need);
+            if (end >= total || (closed && end >= limit)) exhausted = true;
+            if (!active && !pending && !start) {
+                const unsigned i = base + (unsigned)__popc(need & ((1u << lane) - 1u));
+                if (i < limit) { idx = i; start = true; }
+                else if (!closed && i < total) idx = i | kReserved;
+            }
+        }
+    }
+    return start;
+}
+
+// queue position -> pixel (index into raw, line of the row table, column)
+__device__ __forceinline__ void pixel_of_claim(const EscapeParams& p, unsigned idx, unsigned& pix, int& line, int& ix)
+{
+    if (p.order) {
+        const unsigned band_px = (unsigned)p.width * (unsigned)p.aa;
+        const unsigned slot = idx / band_px, rem = idx - slot * band_px;
+        const unsigned band = __ldcg(&p.order[slot]);
+        const unsigned l = rem / (unsigned)p.width;
+        line = (int)(band * (unsigned)p.aa + l);
+        ix = (int)(rem - l * (unsigned)p.width);
+        pix = (unsigned)line * (unsigned)p.width + (unsigned)ix;
+    } else {
+        pix = idx;
+        line = (int)(idx / (unsigned)p.width);
+        ix = (int)(idx - (unsigned)line * (unsigned)p.width);
+    }
+}
+
+// nobody is iterating: leave, or -- fed plan with reservations outstanding -- wait for the host
+__device__ __forceinline__ bool queue_idle_wait(const EscapeParams& p, unsigned idx)
+{
+    if (!p.feed || !__any_sync(0xffffffffu, (idx & kReserved) != 0u)) return false;
+    __nanosleep(2000);
+    return true;
+}
+
 template <int N>
 __device__ __forceinline__ void load_entry(const CoordTable& t, int i, Num<N>& v)
 {
@@ -366,34 +446,23 @@ escape_mpfr_kernel(const EscapeParams p)
                 }
             }
         } } else
-        if (!exhausted) {
-            const unsigned need = __ballot_sync(0xffffffffu, !active);
-            if (need) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(p.queue, (unsigned)__popc(need));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base + (unsigned)__popc(need) >= total) exhausted = true;
-                if (!active) {
-                    const unsigned idx = base + (unsigned)__popc(need & ((1u << lane) - 1u));
-                    if (idx < total) {
-                        pix = idx;
-                        const int line = (int)(idx / (unsigned)p.width);
-                        const int ix = (int)(idx - (unsigned)line * (unsigned)p.width);
-                        Num<N> x, y, cx, cy;
-                        load_entry<N>(p.xs, ix, x);
-                        load_entry<N>(p.ys, line, y);
-                        if (p.family == FAMILY_JULIA) {
-                            load_entry<N>(p.jc, 0, cx);
-                            load_entry<N>(p.jc, 1, cy);
-                        } else { cx = x; cy = y; }
-                        pixel_init<N>(st, x, y, cx, cy, p.rc, cre_m, cim_m);
-                        active = true;
-                        if (CYC) cycle_save<N>(p, st, cyc);
-                    }
-                }
+        if (!exhausted || (p.feed && __any_sync(0xffffffffu, !active && (pix & kReserved) != 0u))) {
+            if (claim_pixels(p, lane, total, active, pix, exhausted)) {
+                int line, ix;
+                pixel_of_claim(p, pix, pix, line, ix);
+                Num<N> x, y, cx, cy;
+                load_entry<N>(p.xs, ix, x);
+                load_entry<N>(p.ys, line, y);
+                if (p.family == FAMILY_JULIA) {
+                    load_entry<N>(p.jc, 0, cx);
+                    load_entry<N>(p.jc, 1, cy);
+                } else { cx = x; cy = y; }
+                pixel_init<N>(st, x, y, cx, cy, p.rc, cre_m, cim_m);
+                active = true;
+                if (CYC) cycle_save<N>(p, st, cyc);
             }
         }
-        if (!__any_sync(0xffffffffu, active)) break;
+        if (!__any_sync(0xffffffffu, active)) { if (queue_idle_wait(p, pix)) continue; break; }
 
         // ---- iterate ------------------------------------------------------
         uint32_t rare_seen = 0;
@@ -506,33 +575,22 @@ escape_gmp_kernel(const EscapeParams p)
             if (lane == 0) stop = *p.cancel == p.gen;
             if (__shfl_sync(0xffffffffu, stop, 0)) break;
         }
-        if (!exhausted) {
-            const unsigned need = __ballot_sync(0xffffffffu, !active);
-            if (need) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(p.queue, (unsigned)__popc(need));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base + (unsigned)__popc(need) >= total) exhausted = true;
-                if (!active) {
-                    const unsigned idx = base + (unsigned)__popc(need & ((1u << lane) - 1u));
-                    if (idx < total) {
-                        pix = idx;
-                        const int line = (int)(idx / (unsigned)p.width);
-                        const int ix = (int)(idx - (unsigned)line * (unsigned)p.width);
-                        Mpf<NL> x, y, cx, cy;
-                        load_mpf_entry<NL>(p.xs, ix, x);
-                        load_mpf_entry<NL>(p.ys, line, y);
-                        if (p.family == FAMILY_JULIA) {
-                            load_mpf_entry<NL>(p.jc, 0, cx);
-                            load_mpf_entry<NL>(p.jc, 1, cy);
-                        } else { cx = x; cy = y; }
-                        gmp_pixel_init<NL>(st, x, y, cx, cy);
-                        active = true;
-                    }
-                }
+        if (!exhausted || (p.feed && __any_sync(0xffffffffu, !active && (pix & kReserved) != 0u))) {
+            if (claim_pixels(p, lane, total, active, pix, exhausted)) {
+                int line, ix;
+                pixel_of_claim(p, pix, pix, line, ix);
+                Mpf<NL> x, y, cx, cy;
+                load_mpf_entry<NL>(p.xs, ix, x);
+                load_mpf_entry<NL>(p.ys, line, y);
+                if (p.family == FAMILY_JULIA) {
+                    load_mpf_entry<NL>(p.jc, 0, cx);
+                    load_mpf_entry<NL>(p.jc, 1, cy);
+                } else { cx = x; cy = y; }
+                gmp_pixel_init<NL>(st, x, y, cx, cy);
+                active = true;
             }
         }
-        if (!__any_sync(0xffffffffu, active)) break;
+        if (!__any_sync(0xffffffffu, active)) { if (queue_idle_wait(p, pix)) continue; break; }
         for (int k = 0; k < p.chunk; ++k) {
             if (active) {
                 const bool esc = gmp_pixel_step<NL>(st, abs_im, abs_re);
@@ -599,33 +657,22 @@ escape_gmpf_kernel(const EscapeParams p)
             if (lane == 0) stop = *p.cancel == p.gen;
             if (__shfl_sync(0xffffffffu, stop, 0)) break;
         }
-        if (!exhausted) {
-            const unsigned need = __ballot_sync(0xffffffffu, !active);
-            if (need) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(p.queue, (unsigned)__popc(need));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base + (unsigned)__popc(need) >= total) exhausted = true;
-                if (!active) {
-                    const unsigned idx = base + (unsigned)__popc(need & ((1u << lane) - 1u));
-                    if (idx < total) {
-                        pix = idx;
-                        const int line = (int)(idx / (unsigned)p.width);
-                        const int ix = (int)(idx - (unsigned)line * (unsigned)p.width);
-                        GF<NW> x, y, cx, cy;
-                        load_gf_entry<NW>(p.xs, ix, x);
-                        load_gf_entry<NW>(p.ys, line, y);
-                        if (p.family == FAMILY_JULIA) {
-                            load_gf_entry<NW>(p.jc, 0, cx);
-                            load_gf_entry<NW>(p.jc, 1, cy);
-                        } else { cx = x; cy = y; }
-                        gf_pixel_init<NW>(st, x, y, cx, cy, cre_m, cim_m);
-                        active = true;
-                    }
-                }
+        if (!exhausted || (p.feed && __any_sync(0xffffffffu, !active && (pix & kReserved) != 0u))) {
+            if (claim_pixels(p, lane, total, active, pix, exhausted)) {
+                int line, ix;
+                pixel_of_claim(p, pix, pix, line, ix);
+                GF<NW> x, y, cx, cy;
+                load_gf_entry<NW>(p.xs, ix, x);
+                load_gf_entry<NW>(p.ys, line, y);
+                if (p.family == FAMILY_JULIA) {
+                    load_gf_entry<NW>(p.jc, 0, cx);
+                    load_gf_entry<NW>(p.jc, 1, cy);
+                } else { cx = x; cy = y; }
+                gf_pixel_init<NW>(st, x, y, cx, cy, cre_m, cim_m);
+                active = true;
             }
         }
-        if (!__any_sync(0xffffffffu, active)) break;
+        if (!__any_sync(0xffffffffu, active)) { if (queue_idle_wait(p, pix)) continue; break; }
         for (int k = 0; k < p.chunk; ++k) {
             if (active) {
                 const bool esc = gf_pixel_step<NW>(st, cre_m, cim_m, scr, abs_im, abs_re);

@@ -57,6 +57,10 @@ struct EscapeParams {
     unsigned int* park_smslot;      // [4096] phase 1: arrivals per SM, dense SM numbers   } zeroed by
     unsigned int* park_claimed;     // [park_cap / 32] phase 1: group of 32 handed out      } park_sort_kernel
     int park_sms;                   // SMs of the device
+    // Fed plans (several devices on one image, mdzcuda.cu "band scheduler"): the queue runs over slots of
+    // one band each that the host fills while the kernel runs.  nullptr: static plan, queue position = pixel.
+    const unsigned int* order;              // [slot] -> band
+    const volatile unsigned int* feed;      // [0] slots filled so far, [1] == gen: no more will come
     Ld64Masks ld_masks;     // ld64_masks(fractal), filled in by the host so that the hot loop reads them as constants
 };
 

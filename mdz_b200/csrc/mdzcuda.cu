@@ -3,7 +3,10 @@
 // count, progress / cancel plumbing and the IMAD peak microbenchmark.
 //
 // There is deliberately no CPU implementation of the escape-time loop in this
-// library: if CUDA is unavailable every entry point fails with an error text.
+// library: if CUDA is unavailable every entry point here fails with an error text.
+// (The rth_* layer, rth.cpp, then runs the line callback the HOST installed -- the
+// reference's own interface, src/render_threads.c:375-377 -- and counts those lines in
+// mdzcuda_fallback_lines().)
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -18,9 +21,13 @@
 #include <mutex>
 #include <map>
 
+#include <atomic>
+
 #include "../../include/mdzcuda.h"
 #include "escape_params.cuh"
 #include "mp_convert.h"
+#include "band_grants.h"
+#include "mdz_run.h"
 
 using namespace mdz;
 
@@ -350,6 +357,16 @@ struct mdzcuda_plan {
     uint32_t* d_park = nullptr;         // parked pixel states + reading order + claim words, allocated at the first launch that parks
     size_t park_words = 0;
     bool gmp = false;
+    // fed plan (band scheduler): queue slots filled by the host while the kernel runs
+    bool fed = false;
+    unsigned int* d_order = nullptr;    // [nbands] slot -> band
+    unsigned int* d_feed = nullptr;     // [0] slots filled, [1] generation of the launch that is closed
+    unsigned int* h_stage = nullptr;    // pinned staging: [nbands] order entries + [4] control words
+    size_t h_stage_cap = 0;
+    int granted = 0;                    // slots filled so far in the current launch
+    bool closed = false;
+    unsigned int claimed = 0;           // queue counter as of the last poll
+    cudaStream_t own = nullptr;         // the plan's own non-blocking launch stream (mdzcuda_plan_stream)
     mdzcuda_kernel_info info;
     unsigned int* h_pinned = nullptr;   // 4 words of pinned staging
     uint32_t* d_palette = nullptr;      // 256 entries
@@ -383,6 +400,36 @@ static int gmp_smem_words(int nl)
 }
 static kernel_fn kernel_for_limbs(int n, int cyc = 0) { return mdz_kernel_mpfr(n, cyc); }
 static int smem_words_for_limbs(int n) { return mdz_smem_words_mpfr(n); }
+
+// the kernel that renders this mode / precision (nullptr + error text: none is instantiated)
+static kernel_fn kernel_for_view(const mdzcuda_view* v, int* n32_out)
+{
+    int n32;
+    if (v->mode == MDZCUDA_MODE_LD) n32 = 2;
+    else if (v->mode == MDZCUDA_MODE_MPFR) {
+        if (v->precision < 33) { set_err("MPFR precision below 33 bits is not supported"); return nullptr; }
+        if (v->precision > 32L * 4096) { set_err("MPFR precision %ld: no GPU kernel above %d bits", v->precision, 32 * 4096); return nullptr; }
+        n32 = limbs32_for_prec(v->precision);
+    } else if (v->mode == MDZCUDA_MODE_GMP) {
+        // mpf_init2(p): precision in limbs P = (max(53,p)+127)/64, storage P+1 limbs
+        const long pb = v->precision < 53 ? 53 : v->precision;
+        if (pb > 32L * 4096) { set_err("GMP precision %ld: no GPU kernel", v->precision); return nullptr; }
+        n32 = 2 * (int)((pb + 127) / 64 + 1);
+    }
+    else { set_err("unknown mode %d", v->mode); return nullptr; }
+    kernel_fn fn = v->mode == MDZCUDA_MODE_GMP ? gmp_kernel_for_limbs(n32 / 2) : kernel_for_limbs(n32);
+    if (!fn) { set_err("%s precision %ld needs %d limbs: no GPU kernel instantiated", v->mode == MDZCUDA_MODE_GMP ? "GMP mpf" : "MPFR", v->precision, n32); return nullptr; }
+    *n32_out = n32;
+    return fn;
+}
+
+extern "C" int mdzcuda_view_supported(const mdzcuda_view* v)
+{
+    g_err.clear();
+    if (!v) { set_err("null view"); return 0; }
+    int n32 = 0;
+    return kernel_for_view(v, &n32) != nullptr;
+}
 
 // ---- prologue: MPFR mode (reference src/fractal.c:143-188) ------------------
 static int prologue_mpfr(const mdzcuda_view* v, const std::vector<int>& lines,
@@ -450,15 +497,19 @@ static int prologue_gmp(const mdzcuda_view* v, const std::vector<int>& lines,
     }
     jc.init(n32, 2);
     if (v->family == MDZCUDA_FAMILY_JULIA) {
-        if (!v->julia_re || !v->julia_im) { set_err("julia family needs julia_re/julia_im"); return 0; }
+        if (!(v->gjulia_re && v->gjulia_im) && (!v->julia_re || !v->julia_im)) { set_err("julia family needs julia_re/julia_im"); return 0; }
         // mpfr_to_gmp (coords.c:13-18): through the decimal text my_mpfr_to_str prints,
         // i.e. mpfr_snprintf "%.Re" (my_mpfr_to_str.c:68) -- one significant digit with
         // MPFR >= 4 (SURVEY finding 3); reproduced literally, as the drop-in must
-        char buf[4097];
-        mpfr_snprintf(buf, 4096, "%.Re", v->julia_re);
-        mpf_set_str(x, buf, 10);
-        mpfr_snprintf(buf, 4096, "%.Re", v->julia_im);
-        mpf_set_str(y, buf, 10);
+        // A host that keeps the constant as mpf (or wants another conversion) passes it directly.
+        if (v->gjulia_re && v->gjulia_im) { mpf_set(x, v->gjulia_re); mpf_set(y, v->gjulia_im); }
+        else {
+            char buf[4097];
+            mpfr_snprintf(buf, 4096, "%.Re", v->julia_re);
+            mpf_set_str(x, buf, 10);
+            mpfr_snprintf(buf, 4096, "%.Re", v->julia_im);
+            mpf_set_str(y, buf, 10);
+        }
         jc.set_mpf(0, x); jc.set_mpf(1, y);
     }
     mpf_clear(img_rw); mpf_clear(img_xmin); mpf_clear(width);
@@ -543,27 +594,18 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
     if (v->real_width < 1 || v->real_height < 1 || v->aa_factor < 1 ||
         v->real_height % v->aa_factor != 0) { set_err("bad image size / aa factor"); return nullptr; }
     if (v->depth < 1 || v->depth > 2147483647L) { set_err("depth out of range"); return nullptr; }
-    if ((long long)v->real_width * v->real_height >= (1LL << 32)) { set_err("image too large"); return nullptr; }
+    if ((long long)v->real_width * v->real_height >= (1LL << 31)) { set_err("image too large (2^31 supersamples or more)"); return nullptr; }
     if (band_stride < 1 || band_first < 0) { set_err("bad band partition"); return nullptr; }
     if (!v->xmin || !v->ymax) { set_err("view rect missing"); return nullptr; }
     int ndev = mdzcuda_device_count();
     if (ndev <= 0) { if (g_err.empty()) set_err("no CUDA device"); return nullptr; }
     if (device < 0 || device >= ndev) { set_err("device %d out of range (%d visible)", device, ndev); return nullptr; }
+    if (device >= kMaxDev) { set_err("device %d: this build pools at most %d devices", device, kMaxDev); return nullptr; }
 
-    int n32;
-    if (v->mode == MDZCUDA_MODE_LD) n32 = 2;
-    else if (v->mode == MDZCUDA_MODE_MPFR) {
-        if (v->precision < 33) { set_err("MPFR precision below 33 bits is not supported"); return nullptr; }
-        n32 = limbs32_for_prec(v->precision);
-    } else if (v->mode == MDZCUDA_MODE_GMP) {
-        // mpf_init2(p): precision in limbs P = (max(53,p)+127)/64, storage P+1 limbs
-        const long pb = v->precision < 53 ? 53 : v->precision;
-        n32 = 2 * (int)((pb + 127) / 64 + 1);
-    }
-    else { set_err("unknown mode %d", v->mode); return nullptr; }
+    int n32 = 0;
+    kernel_fn fn = kernel_for_view(v, &n32);
+    if (!fn) return nullptr;
     const bool gmp = v->mode == MDZCUDA_MODE_GMP;
-    kernel_fn fn = gmp ? gmp_kernel_for_limbs(n32 / 2) : kernel_for_limbs(n32);
-    if (!fn) { set_err("precision %ld needs %d limbs: no kernel instantiated", v->precision, n32); return nullptr; }
 
     mdzcuda_plan* pl = new mdzcuda_plan();
     pl->view = *v;
@@ -599,6 +641,8 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
             const size_t o_count = ar.reserve((size_t)pl->nbands + 1);
             const size_t o_flag = ar.reserve((size_t)pl->nbands + 1);
             const size_t o_cancel = ar.reserve(4);
+            const size_t o_feed = ar.reserve(4);
+            const size_t o_order = ar.reserve((size_t)pl->nbands + 1);
             CUDA_OKP(pool_alloc(device, (void**)&pl->d_arena, ar.words * sizeof(uint32_t)));
             table_image.swap(ar.host); table_bytes = table_words * sizeof(uint32_t);
             uint32_t* b = pl->d_arena;
@@ -609,12 +653,15 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
             pl->d_band_count = b + o_count;
             pl->d_band_flag = b + o_flag;
             pl->d_cancel = b + o_cancel;
+            pl->d_feed = b + o_feed;
+            pl->d_order = b + o_order;
             pl->zero_words = ar.words - o_ctrl;     // everything from the control words on, once, at create
             pl->reset_words = o_flag - o_ctrl;      // per launch: queue counter and band counters only
         }
         size_t npx = (size_t)pl->local_lines * v->real_width;
         CUDA_OKP(pool_alloc(device, (void**)&pl->d_raw, (npx ? npx : 1) * sizeof(int32_t)));
         CUDA_OKP(pool_stream(device, &pl->side));
+        CUDA_OKP(pool_stream(device, &pl->own));
         // Control words, band counters and flags start at zero.  On the side stream, and waited
         // for: the polls run on that stream, which is not ordered against the caller's, and a
         // recycled arena still holds the previous plan's flags (a cudaMemset on the default
@@ -650,6 +697,68 @@ extern "C" int mdzcuda_plan_set_cycle_detection(mdzcuda_plan* pl, int on)
     pl->cycle = on ? 1 : 0;
     return 1;
 }
+
+// ---------------------------------------------------------------------------
+// Fed plans: the device side is escape_kernel.cuh "The pixel queue"; the policy is band_grants.h.
+// ---------------------------------------------------------------------------
+extern "C" void* mdzcuda_plan_stream(mdzcuda_plan* pl) { return pl ? (void*)pl->own : nullptr; }
+
+extern "C" int mdzcuda_plan_set_fed(mdzcuda_plan* pl, int on)
+{
+    if (!pl) { set_err("null plan"); return 0; }
+    if (on && (pl->band_first != 0 || pl->band_stride != 1)) { set_err("a fed plan must cover the whole image (band_first 0, band_stride 1)"); return 0; }
+    if (on && !pl->h_stage) {
+        void* q = nullptr; size_t cap = 0;
+        CUDA_OK(cudaSetDevice(pl->device));
+        CUDA_OK(pool_pinned_buf(pl->device, &q, &cap, ((size_t)pl->nbands + 8) * sizeof(unsigned int)));
+        pl->h_stage = (unsigned int*)q; pl->h_stage_cap = cap;
+    }
+    pl->fed = on != 0;
+    return 1;
+}
+
+extern "C" int mdzcuda_plan_feed(mdzcuda_plan* pl, const int* bands, int count, int close)
+{
+    if (!pl) { set_err("null plan"); return 0; }
+    if (!pl->fed) { set_err("not a fed plan"); return 0; }
+    if (count < 0 || pl->granted + count > pl->nbands) { set_err("feed: more bands than the plan has"); return 0; }
+    if (pl->closed) { if (count == 0) return 1; set_err("feed: the launch is closed"); return 0; }
+    CUDA_OK(cudaSetDevice(pl->device));
+    unsigned int* ctl = pl->h_stage + pl->nbands;
+    if (count > 0) {
+        for (int k = 0; k < count; ++k) {
+            if (bands[k] < 0 || bands[k] >= pl->nbands) { set_err("feed: band %d out of range", bands[k]); return 0; }
+            pl->h_stage[pl->granted + k] = (unsigned int)bands[k];
+        }
+        // order[] first, then the limit, then the close word: the kernel reads them in the opposite order
+        CUDA_OK(cudaMemcpyAsync(pl->d_order + pl->granted, pl->h_stage + pl->granted, (size_t)count * sizeof(unsigned int),
+                                cudaMemcpyHostToDevice, pl->side));
+        pl->granted += count;
+        ctl[0] = (unsigned int)pl->granted;
+        CUDA_OK(cudaMemcpyAsync(pl->d_feed + 0, ctl + 0, sizeof(unsigned int), cudaMemcpyHostToDevice, pl->side));
+    }
+    if (close) {
+        ctl[1] = pl->gen;
+        CUDA_OK(cudaMemcpyAsync(pl->d_feed + 1, ctl + 1, sizeof(unsigned int), cudaMemcpyHostToDevice, pl->side));
+        pl->closed = true;
+    }
+    CUDA_OK(cudaStreamSynchronize(pl->side));
+    return 1;
+}
+
+// pixels granted to the current launch that no lane had claimed at the last mdzcuda_plan_poll_bands
+extern "C" long long mdzcuda_plan_backlog(mdzcuda_plan* pl)
+{
+    if (!pl) { set_err("null plan"); return -1; }
+    const long long band_px = (long long)pl->view.real_width * pl->view.aa_factor;
+    const long long granted = (pl->fed ? (long long)pl->granted : (long long)pl->nbands) * band_px;
+    const long long b = granted - (long long)pl->claimed;
+    return b > 0 ? b : 0;
+}
+
+static std::atomic<long> g_fallback_lines(0);
+void mdz_count_fallback_lines(long n) { g_fallback_lines += n; }
+extern "C" long mdzcuda_fallback_lines(void) { return g_fallback_lines.load(); }
 
 // Order in which phase 1 reads the parked list: a counting sort by iteration count (2048 buckets over
 // 0..depth), one block.  Pixels that entered the list with about the same count have about the same
@@ -727,6 +836,14 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
     cudaStream_t st = (cudaStream_t)cuda_stream;
     CUDA_OK(cudaSetDevice(pl->device));
     CUDA_OK(cudaMemsetAsync(pl->d_ctrl, 0, pl->reset_words * sizeof(uint32_t), st));   // queue, counters, flags
+    pl->claimed = 0;
+    if (pl->fed) {
+        // the fill count restarts at zero; on the side stream, where the feeds will follow it in order
+        // (the close word carries the launch generation and needs no reset)
+        pl->granted = 0; pl->closed = false;
+        CUDA_OK(cudaMemsetAsync(pl->d_feed, 0, sizeof(unsigned int), pl->side));
+        CUDA_OK(cudaStreamSynchronize(pl->side));
+    }
     {
         // test hook: fill the iteration buffer with a pattern no render produces, so that a band
         // delivered before it was complete shows up deterministically (tests/test_parity_gpu.py)
@@ -756,6 +873,8 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         p.spec = pl->spec;
         if (p.spec == 1) { static const int forced = [] { const char* e = getenv("MDZCUDA_SPEC_LEVEL"); return e && *e ? atoi(e) : 1; }(); p.spec = forced; }   // A/B: 2 / 3 pin level 1 / 2
         p.colour = pl->colour;
+        p.order = pl->fed ? pl->d_order : nullptr;
+        p.feed = pl->fed ? (const volatile unsigned int*)pl->d_feed : nullptr;
         p.ld_masks.im_keep = p.fractal == FRACTAL_BURNING_SHIP ? 0u : 1u;           // ld64_step.cuh: ld64_masks
         p.ld_masks.re_and = p.fractal == FRACTAL_VARIANT ? 1u : 0u;
         p.ld_masks.re_xor = p.fractal == FRACTAL_GENERALIZED_CELTIC ? 0u : 1u;
@@ -792,7 +911,7 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         p.park_smslot = nullptr; p.park_claimed = nullptr; p.park_sms = 1;
         static const int park_env = [] { const char* e = getenv("MDZCUDA_PARK"); return e && *e ? atoi(e) : -1; }();
         const int park_mode = pl->park >= 0 ? pl->park : park_env;
-        const bool park = !pl->gmp && pl->n32 <= kParkMaxLimbs && (park_mode > 0 || (park_mode < 0 && npx >= 2 * grid * kBlock));
+        const bool park = !pl->gmp && !pl->fed && pl->n32 <= kParkMaxLimbs && (park_mode > 0 || (park_mode < 0 && npx >= 2 * grid * kBlock));
         if (park) {
             const size_t cap = (size_t)grid * kBlock;
             const size_t state_words = (size_t)(6 * pl->n32 + 9) * cap;
@@ -887,7 +1006,9 @@ extern "C" int mdzcuda_plan_poll_bands(mdzcuda_plan* pl, unsigned char* flags_ho
     // the poll needs no ordering against the reset that the launch enqueues on the caller's stream.
     if (cudaMemcpyAsync(pl->h_flags.data(), pl->d_band_flag, (size_t)pl->nbands * sizeof(unsigned int),
                         cudaMemcpyDeviceToHost, pl->side) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(pl->h_pinned + 4, pl->d_ctrl, sizeof(unsigned int), cudaMemcpyDeviceToHost, pl->side) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(pl->side) != cudaSuccess) return -1;
+    pl->claimed = pl->h_pinned[4];
     int done = 0;
     const unsigned int gen = pl->gen;
     for (int i = 0; i < pl->nbands; ++i) { const int c = gen != 0 && pl->h_flags[i] == gen; flags_host[i] = (unsigned char)c; done += c; }
@@ -982,8 +1103,11 @@ extern "C" void mdzcuda_plan_destroy(mdzcuda_plan* pl)
     DevPool& P = g_pool[pl->device];
     pool_free(pl->device, pl->d_palette); pool_free(pl->device, pl->d_rgb);
     pool_free(pl->device, pl->d_raw); pool_free(pl->device, pl->d_arena); pool_free(pl->device, pl->d_cycle); pool_free(pl->device, pl->d_park);
+    if (pl->own) cudaStreamSynchronize(pl->own);
+    pool_pinned_buf_free(pl->device, pl->h_stage, pl->h_stage_cap);
     {
         std::lock_guard<std::mutex> lock(P.mu);
+        if (pl->own) P.streams.push_back(pl->own);
         if (pl->side) P.streams.push_back(pl->side);
         if (pl->done_ev) P.events.push_back(pl->done_ev);
         if (pl->h_pinned) P.pinned.push_back(pl->h_pinned);
@@ -991,36 +1115,54 @@ extern "C" void mdzcuda_plan_destroy(mdzcuda_plan* pl)
     delete pl;
 }
 
-// Copy the bands of running plans into raw_host as they complete, so that by the time
-// the kernels end only the last few bands are still on the device (the D2H of an
-// 8 MB raw_data otherwise adds 2-3 ms to a 60 ms render).  Same mechanism the rth_*
-// layer uses to feed rth_process_lines_rendered, minus the publishing.
-static int deliver_bands(std::vector<mdzcuda_plan*>& plans, int32_t* raw_host)
+// ---------------------------------------------------------------------------
+// The render driver: launched plans -> the caller's raw_data.
+//
+// Finished bands are copied into raw_host while the kernels are still running, so that by the time they
+// end only the last few are still on the device (the D2H of an 8 MB raw_data otherwise adds 2-3 ms to a
+// 60 ms render), and -- rth.cpp -- so that MDZ's consumer loop sees lines arrive progressively.
+//
+// Band scheduler (several devices, one image; SURVEY 8e "Partitioning").  Every device holds a *fed* plan
+// of the whole image whose persistent kernel eats a queue of band slots that this loop fills while it
+// runs: a device is given the next chunk of bands (band_grants.h: large first, small at the end) whenever
+// the unclaimed part of its queue falls below one grid's worth of pixels.  A device that is slow -- shared
+// with another job, or holding the deep part of the image -- asks less often; nothing is decided up front.
+// The reference does the same with lines and a mutex (src/render_threads.c:360-393).
+// ---------------------------------------------------------------------------
+static int run_plans(std::vector<mdzcuda_plan*>& plans, int32_t* raw_host, const mdz_run_hooks* hooks, mdz::BandGrants* grants)
 {
     const int n = (int)plans.size();
     std::vector<std::vector<unsigned char> > flags(n), seen(n);
-    std::vector<int> left(n, 0);
+    std::vector<int> delivered(n, 0);
     int remaining = 0;
     for (int i = 0; i < n; ++i) {
         const int nb = plans[i]->nbands;
         flags[i].assign((size_t)nb + 1, 0); seen[i].assign((size_t)nb + 1, 0);
-        left[i] = nb; remaining += nb;
+        if (!grants) remaining += nb;
     }
-    const struct timespec nap = { 0, 250 * 1000 };
+    if (grants) remaining = grants->total;
+    const int min_run_cfg = hooks && hooks->min_run > 0 ? hooks->min_run : 16;
+    const struct timespec nap = { 0, 200 * 1000 };
+    int rc = 1;
     while (remaining > 0) {
+        if (hooks && hooks->should_stop && hooks->should_stop(hooks->user)) {
+            for (int i = 0; i < n; ++i) mdzcuda_plan_cancel(plans[i]);
+            rc = 2;
+            break;
+        }
         bool progress = false;
         for (int i = 0; i < n; ++i) {
-            if (!left[i]) continue;
             mdzcuda_plan* pl = plans[i];
             const int nb = pl->nbands;
+            const int expect = pl->fed ? pl->granted : nb;       // bands this plan is to deliver (so far)
+            if (!pl->fed && delivered[i] == nb) continue;
             CUDA_OK(cudaSetDevice(pl->device));
             const cudaError_t q = cudaEventQuery(pl->done_ev);
             if (q != cudaSuccess && q != cudaErrorNotReady) { set_err("kernel failed: %s", cudaGetErrorString(q)); return 0; }
             const bool finished = q == cudaSuccess;
-            if (finished) memset(flags[i].data(), 1, (size_t)nb);     // (a cancelled launch leaves its unfinished bands as they are)
-            else if (mdzcuda_plan_poll_bands(pl, flags[i].data()) < 0) return 0;
+            if (mdzcuda_plan_poll_bands(pl, flags[i].data()) < 0) return 0;
             // whole runs only, and not in crumbs: each copy costs ~20 us of driver time
-            const int min_run = finished ? 1 : 16;
+            const int min_run = finished ? 1 : min_run_cfg;
             for (int b = 0; b < nb;) {
                 if (!flags[i][b] || seen[i][b]) { ++b; continue; }
                 int e = b;
@@ -1028,56 +1170,109 @@ static int deliver_bands(std::vector<mdzcuda_plan*>& plans, int32_t* raw_host)
                 if (e - b >= min_run) {
                     if (!mdzcuda_plan_fetch_bands(pl, raw_host, b, e - b)) return 0;
                     for (int k = b; k < e; ++k) seen[i][k] = 1;
-                    left[i] -= e - b; remaining -= e - b;
+                    delivered[i] += e - b; remaining -= e - b;
+                    if (hooks && hooks->bands_ready)
+                        hooks->bands_ready(hooks->user, pl->band_first + b * pl->band_stride, e - b, pl->band_stride);
                     progress = true;
                 }
                 b = e;
+            }
+            if (finished && delivered[i] < expect && (!pl->fed || pl->closed)) {
+                // the launch is over and a band it owed is not flagged: a kernel that died without a sticky error
+                set_err("device %d: the kernel ended with %d of %d bands missing", pl->device, expect - delivered[i], expect);
+                return 0;
+            }
+            if (grants && !pl->closed) {
+                const long long band_px = (long long)pl->view.real_width * pl->view.aa_factor;
+                const long long low_water = (long long)pl->info.grid_blocks * kBlock;
+                long long backlog = mdzcuda_plan_backlog(pl);
+                grants->progress(i, (double)pl->claimed / (double)band_px);
+                while (backlog < low_water && grants->remaining() > 0) {
+                    int first = 0;
+                    const int cnt = grants->take(i, &first);
+                    std::vector<int> list((size_t)cnt);
+                    for (int k = 0; k < cnt; ++k) list[k] = first + k;
+                    if (!mdzcuda_plan_feed(pl, list.data(), cnt, 0)) return 0;
+                    backlog += cnt * band_px;
+                    progress = true;
+                }
+                if (grants->remaining() == 0)
+                    for (int j = 0; j < n; ++j)
+                        if (!plans[j]->closed && !mdzcuda_plan_feed(plans[j], nullptr, 0, 1)) return 0;
             }
         }
         if (!progress && remaining > 0) nanosleep(&nap, 0);
     }
     for (int i = 0; i < n; ++i) if (!mdzcuda_plan_wait(plans[i])) return 0;
-    return 1;
+    return rc;
 }
 
 extern "C" int mdzcuda_plan_run(mdzcuda_plan* pl, void* cuda_stream, int32_t* raw_host)
 {
     if (!pl || !raw_host) { set_err("null argument"); return 0; }
+    if (pl->fed) { set_err("a fed plan is driven by mdzcuda_render"); return 0; }
     if (!mdzcuda_plan_launch(pl, cuda_stream)) return 0;
     std::vector<mdzcuda_plan*> one(1, pl);
-    return deliver_bands(one, raw_host);
+    return run_plans(one, raw_host, nullptr, nullptr) == 1;
 }
 
-extern "C" int mdzcuda_render(const mdzcuda_view* view, int32_t* raw_host, int ndev, const int* devices)
+int mdz_run_view(const mdzcuda_view* view, int32_t* raw_host, const int* devices, int ndev, const mdz_run_hooks* hooks)
 {
     g_err.clear();
+    if (!view || !raw_host) { set_err("null argument"); return 0; }
     if (ndev < 1) ndev = 1;
+    const int total_bands = view->aa_factor > 0 ? view->real_height / view->aa_factor : 0;
+    if (ndev > total_bands) ndev = total_bands > 0 ? total_bands : 1;
+    const char* sched_env = getenv("MDZCUDA_SCHED");
+    const bool force_static = sched_env && !strcmp(sched_env, "static");
+    const bool dynamic = ndev > 1 && !force_static;
     std::vector<mdzcuda_plan*> plans(ndev, nullptr);
     int ok = 1;
-    if (ndev == 1) {
-        plans[0] = mdzcuda_plan_create(view, devices ? devices[0] : 0, 0, 1);
-        if (!plans[0]) ok = 0;
-    } else {
-        // plan creation runs the prologue; do it per device in parallel host threads
+    {
+        // plan creation runs the O(W+H) prologue; per device in parallel host threads
         std::vector<std::thread> th;
         std::vector<std::string> errs(ndev);
-        for (int i = 0; i < ndev; ++i)
-            th.emplace_back([&, i]() {
-                plans[i] = mdzcuda_plan_create(view, devices ? devices[i] : i, i, ndev);
-                if (!plans[i]) errs[i] = mdzcuda_last_error();
-            });
-        for (auto& t : th) t.join();
+        auto make = [&](int i) {
+            const int dev = devices ? devices[i] : i;
+            plans[i] = dynamic ? mdzcuda_plan_create(view, dev, 0, 1) : mdzcuda_plan_create(view, dev, i, ndev);
+            if (plans[i] && dynamic && !mdzcuda_plan_set_fed(plans[i], 1)) { mdzcuda_plan_destroy(plans[i]); plans[i] = nullptr; }
+            if (!plans[i]) errs[i] = mdzcuda_last_error();
+        };
+        if (ndev == 1) make(0);
+        else {
+            for (int i = 0; i < ndev; ++i) th.emplace_back(make, i);
+            for (auto& t : th) t.join();
+        }
         for (int i = 0; i < ndev; ++i) if (!plans[i]) { ok = 0; set_err("%s", errs[i].c_str()); }
     }
-    for (int i = 0; ok && i < ndev; ++i) ok = mdzcuda_plan_launch(plans[i], nullptr);
+    if (ok && hooks && hooks->cycle_detection >= 0)
+        for (int i = 0; i < ndev; ++i) mdzcuda_plan_set_cycle_detection(plans[i], hooks->cycle_detection);
+    for (int i = 0; ok && i < ndev; ++i) ok = mdzcuda_plan_launch(plans[i], plans[i]->own);
+    int rc = 0;
     if (ok) {
-        std::vector<mdzcuda_plan*> live(plans);
-        ok = deliver_bands(live, raw_host);
+        if (dynamic) {
+            // at least a quarter of a grid's worth of pixels per chunk, so that a grant is worth its two copies
+            const long long band_px = (long long)view->real_width * view->aa_factor;
+            const long long grid_px = (long long)plans[0]->info.grid_blocks * kBlock;
+            long long mc = (grid_px / 4 + band_px - 1) / band_px;
+            mdz::BandGrants grants(total_bands, ndev, (int)(mc < 1 ? 1 : mc));
+            rc = run_plans(plans, raw_host, hooks, &grants);
+        } else rc = run_plans(plans, raw_host, hooks, nullptr);
+        if (rc == 0) for (int i = 0; i < ndev; ++i) mdzcuda_plan_cancel(plans[i]);     // do not leave a fed kernel waiting for bands
     }
     std::string keep = g_err;
     for (int i = 0; i < ndev; ++i) mdzcuda_plan_destroy(plans[i]);
     g_err = keep;
-    return ok;
+    return rc;
+}
+
+extern "C" int mdzcuda_render(const mdzcuda_view* view, int32_t* raw_host, int ndev, const int* devices)
+{
+    mdz_run_hooks h;
+    memset(&h, 0, sizeof h);
+    h.min_run = 16;
+    h.cycle_detection = -1;         // as the plans' default (MDZCUDA_CYCLE_DETECT)
+    return mdz_run_view(view, raw_host, devices, ndev, &h) == 1;
 }
 
 // ---------------------------------------------------------------------------
@@ -1156,3 +1351,56 @@ static double run_imad_peak(int device, int ms)
 
 extern "C" double mdzcuda_imad_peak(int device, int ms) { return run_imad_peak<1>(device, ms); }
 extern "C" double mdzcuda_imad32_peak(int device, int ms) { return run_imad_peak<0>(device, ms); }
+
+// ---------------------------------------------------------------------------
+// Test hook (tests/test_multi_gpu.py): occupy `blocks` SMs of a device for `ms` milliseconds -- one block
+// per SM, each claiming all of the SM's shared memory so that nothing else fits beside it -- to play a
+// device that is busy with someone else's work.  Asynchronous; returns once the kernel is running.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) occupy_kernel(unsigned long long ns, unsigned int* started)
+{
+    extern __shared__ uint32_t hog[];
+    hog[threadIdx.x] = threadIdx.x;
+    if (threadIdx.x == 0) atomicAdd(started, 1u);
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(20000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    } while (t - t0 < ns);
+    if (hog[threadIdx.x] == 0xffffffffu) started[1] = 1u;
+}
+
+extern "C" int mdzcuda_debug_occupy(int device, int blocks, int ms)
+{
+    g_err.clear();
+    CUDA_OK(cudaSetDevice(device));
+    int smem = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CUDA_OK(cudaFuncSetAttribute((const void*)occupy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    static unsigned int* d_started[kMaxDev];
+    static cudaStream_t hog_stream[kMaxDev];
+    if (device >= kMaxDev) { set_err("device out of range"); return 0; }
+    if (!d_started[device]) {
+        CUDA_OK(cudaMalloc((void**)&d_started[device], 8));
+        CUDA_OK(cudaStreamCreateWithFlags(&hog_stream[device], cudaStreamNonBlocking));
+    }
+    CUDA_OK(cudaMemsetAsync(d_started[device], 0, 8, hog_stream[device]));
+    occupy_kernel<<<blocks, 1024, smem, hog_stream[device]>>>((unsigned long long)ms * 1000000ull, d_started[device]);
+    CUDA_OK(cudaGetLastError());
+    // wait until every block is resident, so that what is launched next finds those SMs taken
+    for (int spin = 0; spin < 20000; ++spin) {
+        unsigned int n = 0;
+        cudaStream_t s2 = nullptr;
+        CUDA_OK(pool_stream(device, &s2));
+        cudaError_t e = cudaMemcpyAsync(&n, d_started[device], 4, cudaMemcpyDeviceToHost, s2);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s2);
+        { std::lock_guard<std::mutex> lock(g_pool[device].mu); g_pool[device].streams.push_back(s2); }
+        CUDA_OK(e);
+        if ((int)n >= blocks) return 1;
+        const struct timespec nap = { 0, 100 * 1000 };
+        nanosleep(&nap, 0);
+    }
+    set_err("occupy kernel did not become resident");
+    return 0;
+}

@@ -23,11 +23,13 @@
 // persistent kernels, and polls band-completion flags, copying finished bands
 // into img->raw_data and publishing them line by line.
 //
-// There is no CPU fallback: if CUDA fails the error goes to stderr, the render
-// ends and rth_ui_wait_for_line_done / rth_process_lines_rendered report
-// completion so that a caller does not hang; raw_data keeps its cleared value.
-// The next_line callback MDZ installs (image_info.c:243-248) is recorded but
-// never called.
+// Views the GPU path cannot render -- a precision or mode no kernel is instantiated
+// for (image_info.c:535 admits 80..99999999 bits), no CUDA device, a CUDA failure --
+// are rendered by the line callback the HOST installed (image_info.c:243-248:
+// fractal_calculate_line / fractal_mpfr_calculate_line / fractal_gmp_calculate_line),
+// from a worker pool that restates render_threads.c:342-393, with one line on stderr;
+// mdzcuda_fallback_lines() counts those lines, and every GPU test asserts it is 0.
+// The library itself still contains no CPU implementation of the loop.
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -40,6 +42,7 @@
 
 #include "../../include/mdz_rth.h"
 #include "../../include/mdzcuda.h"
+#include "mdz_run.h"
 
 enum { RT_STOP = 0x0002, RT_QUIT = 0x0004, RT_RENDERING = 0x0008 };     // render_threads.c:9-14
 
@@ -183,6 +186,83 @@ static std::vector<int> pick_devices()
     return devs;
 }
 
+// ---- the GPU path: mdz_run_view (mdzcuda.cu) with progressive, in-order publication ----------------
+struct RenderCtx {
+    rthdata* rth;
+    std::vector<unsigned char> ready;       // band fetched into img->raw_data
+    int published;
+};
+
+static int hook_should_stop(void* u) { return stop_requested(((RenderCtx*)u)->rth->data); }
+
+// Bands finish out of order on the device(s) but are published strictly in line order: the reference's
+// consumers (render.c:49-92, main_gui.c:533-599) clip their window with the *count* of finished lines,
+// which only describes the image when that count is a prefix of it.
+static void hook_bands_ready(void* u, int first, int count, int stride)
+{
+    RenderCtx* c = (RenderCtx*)u;
+    const int total = (int)c->ready.size();
+    for (int k = 0; k < count; ++k) { const int b = first + k * stride; if (b >= 0 && b < total) c->ready[b] = 1; }
+    while (c->published < total && c->ready[c->published]) publish_band(c->rth, c->published++);
+}
+
+// ---- the host path: the caller's own line callback, as the reference's pool runs it ------------------
+// rth_render + rth_next_line (src/render_threads.c:342-393): N workers take the next band of aa_factor
+// lines under a mutex, call next_line_cb(img, line) for each of its lines (the callback returns 0 when
+// it saw a stop request, fractal.c:113), mark the band rendered and signal.  Used only when the GPU
+// path cannot render the view -- a precision or mode without a kernel, no CUDA device, a CUDA failure --
+// and counted in mdzcuda_fallback_lines().
+struct HostPool {
+    rthdata* rth;
+    std::vector<int> bands;         // bands still to render, in order
+    size_t next;
+    pthread_mutex_t mu;
+};
+
+static void* host_worker(void* ptr)
+{
+    HostPool* hp = (HostPool*)ptr;
+    rthdata* rth = hp->rth;
+    rthpridata* d = rth->data;
+    const int aa = rth->img->aa_factor < 1 ? 1 : rth->img->aa_factor;
+    for (;;) {
+        pthread_mutex_lock(&hp->mu);
+        const size_t k = hp->next++;
+        pthread_mutex_unlock(&hp->mu);
+        if (k >= hp->bands.size()) return 0;
+        const int band = hp->bands[k];
+        for (int i = 0; i < aa; ++i)
+            if (!d->next_line_cb(rth->img, band * aa + i)) return 0;
+        mdz_count_fallback_lines(aa);
+        pthread_mutex_lock(&d->lines_rendered_mutex);
+        d->lines_rendered[band] = 1;
+        d->total_lines_rendered += aa;
+        pthread_cond_signal(&d->lines_rendered_cond);
+        pthread_mutex_unlock(&d->lines_rendered_mutex);
+        if (stop_requested(d)) return 0;
+    }
+}
+
+static void run_host_pool(rthdata* rth, int first_band)
+{
+    HostPool hp;
+    hp.rth = rth; hp.next = 0;
+    for (int b = first_band; b < rth->img->user_height; ++b) hp.bands.push_back(b);
+    pthread_mutex_init(&hp.mu, 0);
+    int nt = rth->thread_count > 0 ? rth->thread_count : 1;
+    if (nt > MAX_THREAD_COUNT) nt = MAX_THREAD_COUNT;
+    std::vector<pthread_t> th((size_t)nt);
+    int made = 0;
+    for (; made < nt; ++made)
+        if (pthread_create(&th[made], 0, host_worker, &hp)) {
+            fprintf(stderr, "\nrender thread #%d creation failed\n", made);       // render_threads.c:308-313
+            break;
+        }
+    if (made == 0) host_worker(&hp);
+    for (int i = 0; i < made; ++i) pthread_join(th[i], 0);
+    pthread_mutex_destroy(&hp.mu);
+}
+
 static void* rth_render_main(void* ptr)
 {
     rthdata* rth = (rthdata*)ptr;
@@ -225,75 +305,47 @@ static void* rth_render_main(void* ptr)
     v.gxmin = img->gxmin; v.gymax = img->gymax; v.gwidth = img->gwidth;
     v.julia_re = img->u.julia.c_re; v.julia_im = img->u.julia.c_im;
 
-    std::vector<int> devs = pick_devices();
-    const int total_bands = img->user_height;
-    if ((int)devs.size() > total_bands) devs.resize(total_bands > 0 ? total_bands : 1);
-    std::vector<mdzcuda_plan*> plans;
+    RenderCtx ctx;
+    ctx.rth = rth;
+    ctx.ready.assign((size_t)(img->user_height > 0 ? img->user_height : 0), 0);
+    ctx.published = 0;
+
     std::string err;
-    if (devs.empty()) err = std::string("no CUDA device: ") + mdzcuda_last_error();
-    for (size_t i = 0; err.empty() && i < devs.size(); ++i) {
-        mdzcuda_plan* p = mdzcuda_plan_create(&v, devs[i], (int)i, (int)devs.size());
-        if (!p) { err = mdzcuda_last_error(); break; }
-        // same raw_data, fewer iterations for interior pixels (include/mdzcuda.h); MDZ's own
-        // callers only ever see the result, so it is on unless MDZCUDA_CYCLE_DETECT=0
-        { const char* e = getenv("MDZCUDA_CYCLE_DETECT"); mdzcuda_plan_set_cycle_detection(p, !(e && *e == '0')); }
-        plans.push_back(p);
+    int rc = 0;
+    static const bool force_host = [] { const char* e = getenv("MDZCUDA_FORCE_HOST"); return e && *e && *e != '0'; }();
+    std::vector<int> devs;
+    if (force_host) err = "MDZCUDA_FORCE_HOST is set";          // test hook: exercise the host path on a GPU box
+    else if (!mdzcuda_view_supported(&v)) err = mdzcuda_last_error();
+    else {
+        devs = pick_devices();
+        if (devs.empty()) err = std::string("no CUDA device: ") + mdzcuda_last_error();
     }
-    for (size_t i = 0; err.empty() && i < plans.size(); ++i)
-        if (!mdzcuda_plan_launch(plans[i], 0)) err = mdzcuda_last_error();
-
     if (err.empty()) {
-        const int ndev = (int)plans.size();
-        std::vector<std::vector<unsigned char> > flags(ndev), seen(ndev);
-        for (int i = 0; i < ndev; ++i) {
-            flags[i].assign(mdzcuda_plan_bands_total(plans[i]) + 1, 0);
-            seen[i].assign(flags[i].size(), 0);
-        }
-        // Bands finish out of order on the device(s) but are published strictly in
-        // line order: the reference's consumers (render.c:49-92, main_gui.c:533-599)
-        // clip their window with the *count* of finished lines, which only works
-        // when that count describes a prefix of the image.
-        std::vector<unsigned char> ready(total_bands + 1, 0);
-        int published = 0, fetched = 0;
-        bool cancelled = false;
-        struct timespec nap = { 0, 200 * 1000 };              // 0.2 ms between polls
-        while (published < total_bands) {
-            if (!cancelled && stop_requested(d)) {
-                for (int i = 0; i < ndev; ++i) mdzcuda_plan_cancel(plans[i]);
-                cancelled = true;
-                break;
-            }
-            bool progress = false;
-            for (int i = 0; i < ndev && err.empty(); ++i) {
-                const int nb = mdzcuda_plan_bands_total(plans[i]);
-                if (mdzcuda_plan_poll_bands(plans[i], flags[i].data()) < 0) { err = mdzcuda_last_error(); break; }
-                for (int b = 0; b < nb;) {
-                    if (!flags[i][b] || seen[i][b]) { ++b; continue; }
-                    int e = b;
-                    while (e < nb && flags[i][e] && !seen[i][e]) ++e;
-                    if (!mdzcuda_plan_fetch_bands(plans[i], img->raw_data, b, e - b)) { err = mdzcuda_last_error(); break; }
-                    for (int k = b; k < e; ++k) { seen[i][k] = 1; ready[i + k * ndev] = 1; ++fetched; }
-                    progress = true;
-                    b = e;
-                }
-            }
-            if (!err.empty()) break;
-            while (published < total_bands && ready[published]) publish_band(rth, published++);
-            if (!progress) nanosleep(&nap, 0);
-        }
-        (void)fetched;
-        for (int i = 0; i < ndev; ++i) mdzcuda_plan_wait(plans[i]);
+        mdz_run_hooks h;
+        h.user = &ctx;
+        h.should_stop = hook_should_stop;
+        h.bands_ready = hook_bands_ready;
+        h.min_run = 1;                                          // progressive delivery
+        // same raw_data, fewer iterations for interior pixels (include/mdzcuda.h); MDZ's own callers only
+        // ever see the result, so it is on unless MDZCUDA_CYCLE_DETECT=0
+        { const char* e = getenv("MDZCUDA_CYCLE_DETECT"); h.cycle_detection = !(e && *e == '0'); }
+        rc = mdz_run_view(&v, img->raw_data, devs.data(), (int)devs.size(), &h);
+        if (rc == 0) err = mdzcuda_last_error();
     }
-    for (size_t i = 0; i < plans.size(); ++i) mdzcuda_plan_destroy(plans[i]);
 
-    if (!err.empty()) {
-        fprintf(stderr, "\nlibmdzcuda: render failed: %s\nlibmdzcuda: there is no CPU fallback; raw_data is left cleared\n", err.c_str());
-        // let a waiting consumer out instead of hanging it
-        pthread_mutex_lock(&d->lines_rendered_mutex);
-        for (int b = 0; b < total_bands; ++b) if (!d->lines_rendered[b]) d->lines_rendered[b] = 1;
-        d->total_lines_rendered = img->real_height;
-        pthread_cond_broadcast(&d->lines_rendered_cond);
-        pthread_mutex_unlock(&d->lines_rendered_mutex);
+    if (!err.empty() && !stop_requested(d)) {
+        if (d->next_line_cb) {
+            // "keep the callback as the CPU fallback when no GPU or an unsupported precision is
+            // present ... a CUDA failure should fall back to the CPU callback rather than change these codes"
+            fprintf(stderr, "\nlibmdzcuda: %s -- rendering %d band(s) with the host's own line callback on %d thread(s)\n",
+                    err.c_str(), img->user_height - ctx.published, rth->thread_count > 0 ? rth->thread_count : 1);
+            run_host_pool(rth, ctx.published);
+        } else {
+            // No callback was ever installed (MDZ always installs one, image_info.c:243-248): nothing can render
+            // this view.  Reporting completion would hand the caller a cleared raw_data as if it were an image.
+            fprintf(stderr, "\nlibmdzcuda: render failed: %s\nlibmdzcuda: no line callback installed to fall back on; giving up\n", err.c_str());
+            exit(EXIT_FAILURE);
+        }
     }
 
     gettimeofday(&d->tv_end, 0);
@@ -377,7 +429,7 @@ extern "C" void rth_ui_wait_until_started(rthdata* rth)
 
 extern "C" void rth_set_next_line_cb(rthdata* rth, int (*next_line_cb)(mdz_image_info*, int))
 {
-    rth->data->next_line_cb = next_line_cb;     // recorded for the caller's sake; never invoked
+    rth->data->next_line_cb = next_line_cb;     // the host's own CPU path: only called when the GPU cannot render the view
 }
 
 extern "C" int rth_process_lines_rendered(rthdata* rth)

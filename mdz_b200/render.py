@@ -26,7 +26,7 @@ class ImageView:
                  user_width=480, user_height=360, aa_factor=1,
                  xmin=None, xmax=None, ymax=None, width=None,
                  gxmin=None, gymax=None, gwidth=None,
-                 julia_re=None, julia_im=None):
+                 julia_re=None, julia_im=None, gjulia_re=None, gjulia_im=None):
         self.use_multi_prec = use_multi_prec
         self.use_rounding = use_rounding
         self.precision = int(precision)
@@ -39,6 +39,7 @@ class ImageView:
         self.xmin, self.xmax, self.ymax, self.width = xmin, xmax, ymax, width
         self.gxmin, self.gymax, self.gwidth = gxmin, gymax, gwidth
         self.julia_re, self.julia_im = julia_re, julia_im
+        self.gjulia_re, self.gjulia_im = gjulia_re, gjulia_im      # optional mpf copy of the constant (GMP mode)
 
     # image_info.c:129-130
     @property
@@ -70,7 +71,7 @@ class ImageView:
             val = getattr(self, name)
             if val is not None:
                 setattr(v, name, val.ptr)
-        for name in ("gxmin", "gymax", "gwidth"):
+        for name in ("gxmin", "gymax", "gwidth", "gjulia_re", "gjulia_im"):
             val = getattr(self, name)
             if val is not None:
                 setattr(v, name, val.ptr)
@@ -79,6 +80,17 @@ class ImageView:
 
 def device_count():
     return _l.lib.mdzcuda_device_count()
+
+
+def fallback_lines():
+    """Lines the rth_* layer rendered through the host's line callback instead of the GPU (0 on a healthy run)."""
+    return int(_l.lib.mdzcuda_fallback_lines())
+
+
+def view_supported(view):
+    """True when a GPU kernel exists for the view's mode and precision."""
+    cv = view.c_view()
+    return bool(_l.lib.mdzcuda_view_supported(C.byref(cv)))
 
 
 def imad_peak(device=0, ms=200, wide=True):

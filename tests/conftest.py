@@ -52,3 +52,13 @@ def ref_lib():
     if lib is None:
         pytest.skip("oracle/_ref/libmdzref.so not available")
     return lib
+
+
+@pytest.fixture(autouse=True)
+def _no_host_fallback(request):
+    """Parity evidence must come from the CUDA kernels: after every GPU test the library's count of lines
+    rendered through the host's line callback (mdzcuda_fallback_lines, rth.cpp) has to be zero."""
+    yield
+    if request.node.get_closest_marker("gpu") is not None:
+        import mdz_b200
+        assert mdz_b200.fallback_lines() == 0, "the rth_* layer fell back to the host callback"

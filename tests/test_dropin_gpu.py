@@ -23,9 +23,11 @@ def run_cmdline(exe, meta, tmp_path):
     src = tmp_path / (meta["name"] + ".mdz")
     src.write_text(meta["mdz_text"])
     out = tmp_path / (meta["name"] + ".ppm")
-    subprocess.run([exe, "-l", str(src), "-w", str(meta["width"]), "-h", str(meta["height"]),
-                    "-A", str(meta["aa"]), "-t", "4", "-R", str(out)],
-                   check=True, stdout=subprocess.DEVNULL, cwd=str(tmp_path), timeout=300)
+    r = subprocess.run([exe, "-l", str(src), "-w", str(meta["width"]), "-h", str(meta["height"]),
+                        "-A", str(meta["aa"]), "-t", "4", "-R", str(out)],
+                       check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, cwd=str(tmp_path), timeout=300)
+    # the image has to come from the CUDA kernels, not from the host callback the drop-in keeps as its fallback
+    assert "libmdzcuda" not in r.stderr, r.stderr[-1000:]
     blob = open(str(out) + ".raw", "rb").read()
     hdr, rest = blob.split(b"\n", 1)
     _, rw, rh, _, _ = hdr.split()
@@ -60,6 +62,7 @@ def test_rth_protocol(tmp_path):
     for prec in (128, 64):
         r = subprocess.run([exe, str(prec)], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and r.stdout.startswith("OK "), r.stdout + r.stderr
+        assert "libmdzcuda" not in r.stderr, r.stderr[-1000:]
         outs.append(r.stdout)
     # the same view rendered twice must give the same checksum
     r2 = subprocess.run([exe, "128"], capture_output=True, text=True, timeout=300)
