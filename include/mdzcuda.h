@@ -131,6 +131,20 @@ int       mdzcuda_plan_feed(mdzcuda_plan*, const int* bands, int count, int clos
 long long mdzcuda_plan_backlog(mdzcuda_plan*);
 void*     mdzcuda_plan_stream(mdzcuda_plan*);
 
+/*
+ * The sequence in which a plan's pixel queue visits its bands.  RASTER (default; what the rth_* layer uses):
+ * top to bottom, the order in which the reference's pool hands lines out (src/render_threads.c:366-369), so
+ * that a consumer sees the image grow from the top.  CENTRE_OUT: from the middle band outwards.  A pixel that
+ * runs to depth occupies its lane for `depth` dependent iterations -- half a second at 512 bits and depth
+ * 100000 -- and a render cannot end before the last one started has finished; deep-zoom views keep their
+ * dense part (a minibrot) near the centre, so starting there takes that latency out of the tail: it is what
+ * mdzcuda_render does (MDZCUDA_ORDER=raster turns it off) and what SURVEY 8(e) asks of the tile order.
+ * raw_data does not depend on it.
+ */
+#define MDZCUDA_ORDER_RASTER     0
+#define MDZCUDA_ORDER_CENTRE_OUT 1
+int mdzcuda_plan_set_order(mdzcuda_plan*, int order);
+
 /* Tunables (before launch): iterations between queue refills (0 = default; a
  * negative value -n means n with the speculative iteration body switched off,
  * for A/B measurements), resident blocks per SM (0 = occupancy maximum). */

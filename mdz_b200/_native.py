@@ -55,6 +55,7 @@ SYMBOLS = {
     "mdzcuda_plan_feed": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int]),
     "mdzcuda_plan_backlog": (C.c_longlong, [C.c_void_p]),
     "mdzcuda_plan_stream": (C.c_void_p, [C.c_void_p]),
+    "mdzcuda_plan_set_order": (C.c_int, [C.c_void_p, C.c_int]),
     "mdzcuda_plan_create": (C.c_void_p, [C.POINTER(View), C.c_int, C.c_int, C.c_int]),
     "mdzcuda_plan_tune": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mdzcuda_plan_set_cycle_detection": (C.c_int, [C.c_void_p, C.c_int]),

@@ -375,7 +375,7 @@ escape_mpfr_kernel(const EscapeParams p)
     bool exhausted = false;         // warp-uniform
     bool first_claim = true;        // phase 1: the first group is chosen by position on the SM
     CycleState cyc; cyc.f0 = 0; cyc.f1 = 0; cyc.next = 0x7fffffff;
-    // warp-uniform: 0 general step, 1 speculative, 2 speculative with wide-gap additions
+    // warp-uniform: 0 general step, 1 speculative, 2 (long double mode only) speculative with the level-2 additions
     // (p.spec: 0 off, 1 adaptive; 2 / 3 pin level 1 / 2 for A/B measurements)
     int spec_level = (SpecLimbs<N>::value && p.spec != 0) ? (p.spec == 3 ? 2 : 1) : 0;
     int spec_pause = 0, spec_backoff = 8;
@@ -513,23 +513,53 @@ escape_mpfr_kernel(const EscapeParams p)
             if (!__any_sync(0xffffffffu, active)) break;
         }
         // ---- adapt: speculation is only worth it while fall-backs are scarce ----
-        // One lane that falls back makes its whole warp run the general step as well, and an
-        // event that a lane meets once in thirty iterations a warp meets in most of them.  So the
-        // measure is the warp's: when more than a quarter of a chunk's iterations had a fall-back,
-        // level 1 (gaps below 31 bits) gives way to level 2 (gaps up to 126 bits, cancellation up
-        // to 62 bits, ~5N instructions more per addition), and level 2 to the general step, each for
-        // an exponentially growing number of chunks (16 ... 4096) before the cheaper one is retried.
+        // One lane that falls back makes its whole warp run the general step as well, and an event that a
+        // lane meets once in three hundred iterations a warp of unsynchronised lanes meets in every tenth.
         if (SpecLimbs<N>::value && p.spec == 1) {
-            if (spec_level != 0) {
-                if (warp_fell * 4 > warp_steps) {
-                    spec_backoff = spec_backoff < 4096 ? spec_backoff * 2 : 4096;
-                    spec_pause = spec_backoff;
-                    spec_level = spec_level == 1 ? 2 : 0;
-                } else if (spec_level == 2) {
-                    if (--spec_pause <= 0) spec_level = 1;          // see whether the narrow one will do again
-                } else if (warp_fell == 0) spec_backoff = 8;
-            } else if (--spec_pause <= 0) {
-                spec_level = 1;
+            if constexpr (N == 2) {
+                // Long double mode, three levels (ld64_step.cuh): when more than a quarter of a chunk's
+                // iterations had a fall-back, level 1 gives way to level 2 (far smaller or zero second
+                // operand, 32..62 cancelled bits; ~10 instructions more per addition) and level 2 to the
+                // general step, each for an exponentially growing number of chunks (16 ... 4096) before the
+                // cheaper one is retried.
+                if (spec_level != 0) {
+                    if (warp_fell * 4 > warp_steps) {
+                        spec_backoff = spec_backoff < 4096 ? spec_backoff * 2 : 4096;
+                        spec_pause = spec_backoff;
+                        spec_level = spec_level == 1 ? 2 : 0;
+                    } else if (spec_level == 2) {
+                        if (--spec_pause <= 0) spec_level = 1;          // see whether the narrow one will do again
+                    } else if (warp_fell == 0) spec_backoff = 8;
+                } else if (--spec_pause <= 0) {
+                    spec_level = 1;
+                }
+            } else {
+                // Multi-limb kernels, two modes.  The speculative step and the general one are ~20 KB of
+                // unrolled code each and the SM's instruction cache holds 32 KB: a warp that alternates
+                // between them -- and makes its neighbours' code miss as well -- runs at half the pace of
+                // either (ncu: 7 stall cycles per issue waiting for instructions; B200, 512 bits, a view next
+                // to a minibrot, where every orbit comes back to ~0 once per period and two iterations in 707
+                // cancel 200 bits / add across a 400-bit gap: 6.8 G it/s alternating, 12.5 general only, 14.5
+                // where nothing falls back).  So a warp speculates only while fewer than one iteration in 32
+                // falls back, judged over windows of 64 iterations; otherwise it runs the general step for an
+                // exponentially growing number of chunks (16 ... 4096) before it looks again.
+                // (one register: spec_pause counts the window's iterations in its low half and its fall-backs in
+                // the high half while speculating, and the chunks left to sit out while not)
+                if (spec_level != 0) {
+                    spec_pause += warp_steps + (warp_fell << 16);
+                    if ((spec_pause & 0xffff) >= 64) {
+                        const int fell = spec_pause >> 16, steps = spec_pause & 0xffff;
+                        spec_pause = 0;
+                        if (fell * 32 > steps) {
+                            spec_backoff = spec_backoff < 4096 ? spec_backoff * 2 : 4096;
+                            spec_pause = spec_backoff;
+                            spec_level = 0;
+                        } else if (fell == 0) spec_backoff = 8;
+                    }
+                } else if (--spec_pause <= 0) {
+                    spec_level = 1;
+                    spec_pause = 0;
+                }
             }
         }
     }

@@ -9,6 +9,7 @@ struct mdz_run_hooks {
     int  (*should_stop)(void* user);                            // polled between deliveries; non-zero cancels the launch
     void (*bands_ready)(void* user, int first_band, int count, int stride); // raw_host now holds bands first, first+stride, ... (any order)
     int  min_run;               // deliver runs of at least this many finished bands while the kernels run (1: at once)
+    int  order;                 // MDZCUDA_ORDER_*: the sequence in which bands are started
     int  cycle_detection;       // 0 / 1: mdzcuda_plan_set_cycle_detection for every plan; -1: the plans' default
 };
 

@@ -359,6 +359,8 @@ struct mdzcuda_plan {
     bool gmp = false;
     // fed plan (band scheduler): queue slots filled by the host while the kernel runs
     bool fed = false;
+    int order_mode = 0;                 // MDZCUDA_ORDER_*: the sequence in which the queue visits the plan's bands
+    bool order_uploaded = false;
     unsigned int* d_order = nullptr;    // [nbands] slot -> band
     unsigned int* d_feed = nullptr;     // [0] slots filled, [1] generation of the launch that is closed
     unsigned int* h_stage = nullptr;    // pinned staging: [nbands] order entries + [4] control words
@@ -703,6 +705,28 @@ extern "C" int mdzcuda_plan_set_cycle_detection(mdzcuda_plan* pl, int on)
 // ---------------------------------------------------------------------------
 extern "C" void* mdzcuda_plan_stream(mdzcuda_plan* pl) { return pl ? (void*)pl->own : nullptr; }
 
+// position -> band for a sequence over n bands: raster, or from the middle outwards (mid, mid+1, mid-1, ...)
+static inline int band_at(int mode, int n, int pos)
+{
+    if (mode != MDZCUDA_ORDER_CENTRE_OUT) return pos;
+    const int mid = n / 2;
+    const int k = (pos + 1) / 2;
+    int b = (pos & 1) ? mid + k : mid - k;
+    // one side runs out first when n is even / at the ends: the rest continues on the other side
+    if (b < 0) b = pos;                 // positions beyond 2*mid: only the upper side is left
+    if (b >= n) b = n - 1 - pos;        // (cannot happen for mid = n / 2, kept for safety)
+    return b;
+}
+
+extern "C" int mdzcuda_plan_set_order(mdzcuda_plan* pl, int mode)
+{
+    if (!pl) { set_err("null plan"); return 0; }
+    if (mode != MDZCUDA_ORDER_RASTER && mode != MDZCUDA_ORDER_CENTRE_OUT) { set_err("unknown order %d", mode); return 0; }
+    if (pl->order_mode != mode) pl->order_uploaded = false;
+    pl->order_mode = mode;
+    return 1;
+}
+
 extern "C" int mdzcuda_plan_set_fed(mdzcuda_plan* pl, int on)
 {
     if (!pl) { set_err("null plan"); return 0; }
@@ -714,6 +738,7 @@ extern "C" int mdzcuda_plan_set_fed(mdzcuda_plan* pl, int on)
         pl->h_stage = (unsigned int*)q; pl->h_stage_cap = cap;
     }
     pl->fed = on != 0;
+    pl->order_uploaded = false;
     return 1;
 }
 
@@ -873,7 +898,15 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         p.spec = pl->spec;
         if (p.spec == 1) { static const int forced = [] { const char* e = getenv("MDZCUDA_SPEC_LEVEL"); return e && *e ? atoi(e) : 1; }(); p.spec = forced; }   // A/B: 2 / 3 pin level 1 / 2
         p.colour = pl->colour;
-        p.order = pl->fed ? pl->d_order : nullptr;
+        if (!pl->fed && pl->order_mode != MDZCUDA_ORDER_RASTER && !pl->order_uploaded) {
+            // a static plan that visits its bands in another sequence: the slot table, once
+            std::vector<unsigned int> seq((size_t)pl->nbands);
+            for (int k = 0; k < pl->nbands; ++k) seq[(size_t)k] = (unsigned int)band_at(pl->order_mode, pl->nbands, k);
+            CUDA_OK(cudaMemcpyAsync(pl->d_order, seq.data(), seq.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, pl->side));
+            CUDA_OK(cudaStreamSynchronize(pl->side));
+            pl->order_uploaded = true;
+        }
+        p.order = (pl->fed || pl->order_mode != MDZCUDA_ORDER_RASTER) ? pl->d_order : nullptr;
         p.feed = pl->fed ? (const volatile unsigned int*)pl->d_feed : nullptr;
         p.ld_masks.im_keep = p.fractal == FRACTAL_BURNING_SHIP ? 0u : 1u;           // ld64_step.cuh: ld64_masks
         p.ld_masks.re_and = p.fractal == FRACTAL_VARIANT ? 1u : 0u;
@@ -1131,6 +1164,7 @@ extern "C" void mdzcuda_plan_destroy(mdzcuda_plan* pl)
 // ---------------------------------------------------------------------------
 static int run_plans(std::vector<mdzcuda_plan*>& plans, int32_t* raw_host, const mdz_run_hooks* hooks, mdz::BandGrants* grants)
 {
+    const int order_mode = hooks ? hooks->order : MDZCUDA_ORDER_RASTER;
     const int n = (int)plans.size();
     std::vector<std::vector<unsigned char> > flags(n), seen(n);
     std::vector<int> delivered(n, 0);
@@ -1191,7 +1225,7 @@ static int run_plans(std::vector<mdzcuda_plan*>& plans, int32_t* raw_host, const
                     int first = 0;
                     const int cnt = grants->take(i, &first);
                     std::vector<int> list((size_t)cnt);
-                    for (int k = 0; k < cnt; ++k) list[k] = first + k;
+                    for (int k = 0; k < cnt; ++k) list[k] = band_at(order_mode, grants->total, first + k);
                     if (!mdzcuda_plan_feed(pl, list.data(), cnt, 0)) return 0;
                     backlog += cnt * band_px;
                     progress = true;
@@ -1247,6 +1281,8 @@ int mdz_run_view(const mdzcuda_view* view, int32_t* raw_host, const int* devices
     }
     if (ok && hooks && hooks->cycle_detection >= 0)
         for (int i = 0; i < ndev; ++i) mdzcuda_plan_set_cycle_detection(plans[i], hooks->cycle_detection);
+    if (ok && hooks && !dynamic)
+        for (int i = 0; i < ndev; ++i) mdzcuda_plan_set_order(plans[i], hooks->order);
     for (int i = 0; ok && i < ndev; ++i) ok = mdzcuda_plan_launch(plans[i], plans[i]->own);
     int rc = 0;
     if (ok) {
@@ -1272,6 +1308,8 @@ extern "C" int mdzcuda_render(const mdzcuda_view* view, int32_t* raw_host, int n
     memset(&h, 0, sizeof h);
     h.min_run = 16;
     h.cycle_detection = -1;         // as the plans' default (MDZCUDA_CYCLE_DETECT)
+    // nobody watches the lines arrive here, so the bands in the middle of the image go first (see mdzcuda_plan_set_order)
+    { const char* e = getenv("MDZCUDA_ORDER"); h.order = (e && !strcmp(e, "raster")) ? MDZCUDA_ORDER_RASTER : MDZCUDA_ORDER_CENTRE_OUT; }
     return mdz_run_view(view, raw_host, devices, ndev, &h) == 1;
 }
 

@@ -326,6 +326,7 @@ static void* rth_render_main(void* ptr)
         h.should_stop = hook_should_stop;
         h.bands_ready = hook_bands_ready;
         h.min_run = 1;                                          // progressive delivery
+        h.order = MDZCUDA_ORDER_RASTER;                         // top to bottom, as the reference's pool hands lines out (render_threads.c:366-369)
         // same raw_data, fewer iterations for interior pixels (include/mdzcuda.h); MDZ's own callers only
         // ever see the result, so it is on unless MDZCUDA_CYCLE_DETECT=0
         { const char* e = getenv("MDZCUDA_CYCLE_DETECT"); h.cycle_detection = !(e && *e == '0'); }

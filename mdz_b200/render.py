@@ -130,6 +130,10 @@ class Plan:
         """Tail compaction: -1 automatic, 0 off, 1 on.  Same raw_data either way."""
         self._chk(_l.lib.mdzcuda_plan_set_parking(self.h, mode), "plan_set_parking")
 
+    def set_order(self, centre_out=True):
+        """Sequence in which the queue visits the plan's bands: raster (default) or from the middle outwards."""
+        self._chk(_l.lib.mdzcuda_plan_set_order(self.h, 1 if centre_out else 0), "plan_set_order")
+
     def launch(self, stream=None):
         self._chk(_l.lib.mdzcuda_plan_launch(self.h, C.c_void_p(stream or 0)), "plan_launch")
 

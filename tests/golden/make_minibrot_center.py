@@ -19,9 +19,8 @@ away from m, and pixels around it escape after about eight times its period.
   4. complex size of the copy, 1 / (beta * lambda^2) with lambda = prod 2 z_k and
      beta = 1 + sum 1 / lambda_k over the periodic orbit (R. Munafo's estimate):
      |size| = 8.80e-122, rotated by 2.18 rad;
-  5. view centre = nucleus + size * (-0.5) - 0.1 * frame height * i: the middle of the copy
-     at 40 % of the frame height, so that the pixels that run to depth are started well
-     before the pixel queue runs dry.
+  5. view centre = nucleus + size * (-0.5): the middle of the copy (its cardioid and disc run from
+     w = 0.25 to w = -1.25) in the middle of the frame.
 Prints the digits pasted into tests/views.py (MINIBROT120, MINIBROT120_NUCLEUS)."""
 import mpmath as mp
 
@@ -94,11 +93,10 @@ def main():
     if c is None:
         raise SystemExit("Newton did not converge")
     s = size_of(c, p)
-    frame_h = mp.mpf("1e-120") * 9 / 16
-    view = c + s * mp.mpf("-0.5") - mp.mpc(0, 1) * frame_h / 10
     print("period", p, "|size|", mp.nstr(abs(s), 8), "arg", mp.nstr(mp.arg(s), 6), "newton steps", its)
     print("nucleus_re", mp.nstr(c.real, 175))
     print("nucleus_im", mp.nstr(c.imag, 175))
+    view = c + s * mp.mpf("-0.5")
     print("cx", mp.nstr(view.real, 175))
     print("cy", mp.nstr(view.imag, 175))
 

@@ -16,7 +16,7 @@ import mdz_b200
 import portpath
 from mdz_b200 import BURNING_SHIP, GENERALIZED_CELTIC
 from refpath import ref_render, ref_render_lines
-from views import config2, config4, config5, deep_embedded_julia
+from views import config2, config4, config4m, config5, deep_embedded_julia
 
 pytestmark = pytest.mark.gpu
 
@@ -67,16 +67,28 @@ def test_config3_deep_embedded_julia_1920x1080_mpfr320(ref_lib):
 
 
 @pytest.mark.parametrize("mode", ["gmp", "mpfr"])
-def test_config4_3840x2160_512bit_deep_zoom(ref_lib, mode):
-    v = config4(3840, 2160, 100000, mode=mode, precision=512)
+def test_config4_3840x2160_512bit_deep_zoom_with_minibrot(ref_lib, mode):
+    """BASELINE configs[3] as SURVEY 8(d) specifies it: a 1e-120 wide view at 512 bits, depth 100000, on a
+    minibrot nucleus, so that part of the frame reaches maxiter (tests/views.py config4m)."""
+    v = config4m(3840, 2160, 100000, mode=mode, precision=512)
     got = mdz_b200.render(v)
-    assert got.min() > 10000 and got.max() < 100000         # everything escapes, deep in the iteration count
-    check_lines(ref_lib, v, got, [0, 1079, 2159])
+    inside = (got == 0).mean()
+    assert 0.015 < inside < 0.03                            # the copy of the set: ~2 % of the frame runs to depth
+    assert got[got > 0].min() > 4000                        # and nothing escapes early, 1e-120 deep
+    check_lines(ref_lib, v, got, [0, 700, 1079, 2159])      # line 700 crosses the minibrot
     if mode == "mpfr":
         p = mdz_b200.Plan(v, 0)
         p.set_cycle_detection(True)
         assert np.array_equal(p.run(), got)
         p.close()
+
+
+def test_config4_round1_view_every_pixel_escapes(ref_lib):
+    """Round 1's config-4 view (on the Misiurewicz point M(23,2), no interior), kept as a second deep view."""
+    v = config4(3840, 2160, 100000, mode="mpfr", precision=512)
+    got = mdz_b200.render(v)
+    assert got.min() > 10000 and got.max() < 100000
+    check_lines(ref_lib, v, got, [0, 1079, 2159])
 
 
 def host_rgb(view, raw, palette, pal_offset, scale, interpolate):

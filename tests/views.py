@@ -83,12 +83,12 @@ def config4(w=3840, h=2160, depth=100000, mode="gmp", precision=512):
 # the period-707 nucleus 2e-61 away from the Misiurewicz point M(7,2) = -1.02004618 + 0.36748404i,
 # size 8.80e-122 (tests/golden/make_minibrot_center.py).  In a 1e-120 wide 16:9 frame the copy of the
 # set covers ~2 % of the pixels (they run to depth); the rest escapes after a few thousand iterations.
-# The centre puts the copy's middle (w = -0.5) at 40 % of the frame height.
-MINIBROT120 = ("-1.020046182259385217091865714835682856485530230077341008574363862552092767130751929513454984842547245021348825939975602029089382380660505102952920023722220432497713672616646017",
-               "0.3674840351832474379034844057678939574299590406994822242761426141816237076291546180151431726933838064685031011319634748791372673372535570498321917665285018130137968923407166453")
+# The view is centred on the middle of the copy (nucleus + size * -0.5).
 MINIBROT120_NUCLEUS = ("-1.020046182259385217091865714835682856485530230077341008574363862552092767130751929513454984842547245021348825939975602029114599645677072089656815758406526854037775728211996565",
                        "0.3674840351832474379034844057678939574299590406994822242761426141816237076291546180151431726933838064685031011319634748792295760419129867435812162956210919108393798335111629735")
 MINIBROT120_PERIOD = 707
+MINIBROT120 = ("-1.020046182259385217091865714835682856485530230077341008574363862552092767130751929513454984842547245021348825939975602029089382380660505102952920023722220432497713672616646017",
+               "0.3674840351832474379034844057678939574299590406994822242761426141816237076291546180151431726933838064685031011319634748791935173372535570498321917665285018130137968923407166453")
 
 
 def config4m(w=3840, h=2160, depth=100000, mode="mpfr", precision=512):

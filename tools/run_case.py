@@ -11,11 +11,23 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np
 import mdz_b200
-from views import make_view, config2, SEAHORSE, deep_embedded_julia
+from views import make_view, config2, SEAHORSE, deep_embedded_julia, config4, config4m, MINIBROT120
 
 
 def case(name, scale=1.0):
     w, h = int(960 * scale), int(540 * scale)
+    if name == "mini":          # the target view (minibrot in the frame), MPFR 512
+        return config4m(w, h, DEPTH or 100000)
+    if name == "minigmp":
+        return config4m(w, h, DEPTH or 100000, mode="gmp")
+    if name == "minioff":       # the same frame moved up by its own height: no interior
+        from mdz_b200.mp import Mpfr
+        import mpmath
+        mpmath.mp.dps = 200
+        cy = mpmath.mpf(MINIBROT120[1]) + mpmath.mpf("0.5625e-120")
+        return make_view(MINIBROT120[0], mpmath.nstr(cy, 180), "1e-120", w, h, precision=512, depth=DEPTH or 100000)
+    if name == "misi":          # round 1's target view: Misiurewicz point, every pixel escapes
+        return config4(w, h, DEPTH or 100000, mode="mpfr")
     if name == "ld":
         return config2(2 * w, 2 * h, 10000)
     if name.startswith("cfg2p"):
@@ -50,12 +62,17 @@ ap.add_argument("--chunk", type=int, default=0)
 ap.add_argument("--bps", type=int, default=0)
 ap.add_argument("--cycle", type=int, default=0, help="1: exact periodicity check on")
 ap.add_argument("--park", type=int, default=-1, help="tail compaction: -1 automatic, 0 off, 1 on")
+ap.add_argument("--depth", type=int, default=0)
+ap.add_argument("--order", type=int, default=0, help="1: bands from the middle outwards")
 ap.add_argument("--stride", type=int, default=1, help="render bands 0, stride, 2*stride, ... only (one rank's share of a strong-scaled render)")
 a = ap.parse_args()
+DEPTH = a.depth
 v = case(a.case, a.scale)
 plan = mdz_b200.Plan(v, 0, 0, a.stride)
 plan.tune(a.chunk, a.bps)
 plan.set_cycle_detection(bool(a.cycle))
+if a.order:
+    plan.set_order(True)
 if a.park != -1:
     plan.set_parking(a.park)
 for i in range(a.reps):
