@@ -42,7 +42,7 @@ class Colour(C.Structure):
 class KernelInfo(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "limbs", "regs_per_thread", "local_bytes", "shared_bytes",
-        "block_threads", "blocks_per_sm", "grid_blocks", "sm_count")]
+        "block_threads", "blocks_per_sm", "grid_blocks", "sm_count", "lanes_per_pixel")]
 
 
 # every symbol include/mdzcuda.h declares: name -> (restype, argtypes)

@@ -61,6 +61,7 @@ struct EscapeParams {
     // one band each that the host fills while the kernel runs.  nullptr: static plan, queue position = pixel.
     const unsigned int* order;              // [slot] -> band
     const volatile unsigned int* feed;      // [0] slots filled so far, [1] == gen: no more will come
+    int prec_bits;          // MPFR precision in bits (the warp-per-pixel kernels derive their rounding position from it)
     Ld64Masks ld_masks;     // ld64_masks(fractal), filled in by the host so that the hot loop reads them as constants
 };
 

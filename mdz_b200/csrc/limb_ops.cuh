@@ -109,12 +109,13 @@ MDZ_HD int clz32(uint32_t x) { return __clz((int)x); }
 // into the next slot of the same array, which no pair has touched yet (it can
 // only hold earlier chain carries), so the single addc cannot overflow.
 // ---------------------------------------------------------------------------
-template <int N>
-MDZ_HD void mul_full(const uint32_t (&a)[N], const uint32_t (&b)[N], uint32_t (&r)[2 * N])
+// T: the limb type -- uint32_t, or (host emulation of the warp-cooperative code, coop_ops.cuh) a vector of 32 lanes
+template <int N, class T = uint32_t>
+MDZ_HD void mul_full(const T (&a)[N], const T (&b)[N], T (&r)[2 * N])
 {
-    uint32_t e[2 * N + 2], o[2 * N + 2];
+    T e[2 * N + 2], o[2 * N + 2];
     MDZ_UNROLL
-    for (int i = 0; i < 2 * N + 2; ++i) { e[i] = 0; o[i] = 0; }
+    for (int i = 0; i < 2 * N + 2; ++i) { e[i] = T(0u); o[i] = T(0u); }
     MDZ_UNROLL
     for (int i = 0; i < N; ++i) {
         MDZ_UNROLL
@@ -135,8 +136,8 @@ MDZ_HD void mul_full(const uint32_t (&a)[N], const uint32_t (&b)[N], uint32_t (&
             }
             const int cp = last + 2;            // where the chain's carry lands
             if (cp < 2 * N) {
-                if ((cp & 1) == 0) e[cp] = addc(e[cp], 0u);
-                else               o[cp - 1] = addc(o[cp - 1], 0u);
+                if ((cp & 1) == 0) e[cp] = addc(e[cp], T(0u));
+                else               o[cp - 1] = addc(o[cp - 1], T(0u));
             }
         }
     }

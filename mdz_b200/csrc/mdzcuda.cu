@@ -253,9 +253,13 @@ struct HostTable {
     void set_mpfr(int i, const __mpfr_struct* v, long prec)
     {
         if (v->_mpfr_exp == MDZ_MPFR_EXP_ZERO) { set_zero_entry(i); return; }
-        uint32_t tmp[64];
-        sig64_to_sig32((const uint64_t*)v->_mpfr_d, prec, tmp, n32);
-        for (int k = 0; k < n32; ++k) m[(size_t)k * count + i] = tmp[k];
+        // the ceil(prec/32) significant limbs go to the top of the entry; a wider entry (the warp-per-pixel
+        // kernels pad to 32 K limbs) is zero below
+        const int n = limbs32_for_prec(prec);
+        std::vector<uint32_t> tmp((size_t)n);
+        sig64_to_sig32((const uint64_t*)v->_mpfr_d, prec, tmp.data(), n);
+        for (int k = 0; k < n32 - n; ++k) m[(size_t)k * count + i] = 0u;
+        for (int k = 0; k < n; ++k) m[(size_t)(n32 - n + k) * count + i] = tmp[(size_t)k];
         long ex = v->_mpfr_exp;
         if (ex < E_MIN) { set_zero_entry(i); return; }
         if (ex > (1 << 28)) ex = (1 << 28);
@@ -331,7 +335,8 @@ static size_t arena_put(Arena& a, const HostTable& h, size_t& om, size_t& oe, si
 struct mdzcuda_plan {
     mdzcuda_view view;          // scalars only are used after create
     int device = 0;
-    int n32 = 0;
+    int n32 = 0;                // limbs per table entry (for the warp-per-pixel kernels: padded to 32 * coop_k)
+    int coop_k = 0;             // 0: one thread per pixel; K: one warp per pixel, K limbs per lane (coop_kernel.cuh)
     int band_first = 0, band_stride = 1, nbands = 0, local_lines = 0;
     std::vector<int> line_map;  // local line -> global line
     DevTable xs, ys, jc;
@@ -382,6 +387,8 @@ typedef void (*kernel_fn)(const EscapeParams);
 // build parallelises: one unrolled kernel per limb count is seconds to minutes of ptxas.
 kernel_fn mdz_kernel_mpfr(int n32, int cyc);    // N = 2..32 words, without / with the periodicity check (kernels_mpfr_*.cu)
 int       mdz_smem_words_mpfr(int n32);
+kernel_fn mdz_kernel_coop(int k);               // K = 2, 4, 6, 8 limbs per lane: 2048 ... 8192 bits  (kernels_coop.cu)
+int       mdz_smem_words_coop(int k);
 kernel_fn mdz_kernel_gmp_clear(int nl);         // NL = 3..10 limbs  (kernels_gmp.cu)
 kernel_fn mdz_kernel_gmp_fast(int nl);          // NL = 4..10 limbs  (kernels_gmpf_*.cu)
 int       mdz_smem_words_gmp_fast(int nl);
@@ -404,18 +411,30 @@ static kernel_fn kernel_for_limbs(int n, int cyc = 0) { return mdz_kernel_mpfr(n
 static int smem_words_for_limbs(int n) { return mdz_smem_words_mpfr(n); }
 
 // the kernel that renders this mode / precision (nullptr + error text: none is instantiated)
-static kernel_fn kernel_for_view(const mdzcuda_view* v, int* n32_out)
+constexpr long kMaxMpfrBits = 8192;
+static kernel_fn kernel_for_view(const mdzcuda_view* v, int* n32_out, int* coop_k_out = nullptr)
 {
     int n32;
+    if (coop_k_out) *coop_k_out = 0;
     if (v->mode == MDZCUDA_MODE_LD) n32 = 2;
     else if (v->mode == MDZCUDA_MODE_MPFR) {
         if (v->precision < 33) { set_err("MPFR precision below 33 bits is not supported"); return nullptr; }
-        if (v->precision > 32L * 4096) { set_err("MPFR precision %ld: no GPU kernel above %d bits", v->precision, 32 * 4096); return nullptr; }
+        if (v->precision > kMaxMpfrBits) { set_err("MPFR precision %ld: no GPU kernel above %d bits", v->precision, kMaxMpfrBits); return nullptr; }
         n32 = limbs32_for_prec(v->precision);
+        if (n32 > 32) {
+            // one warp per pixel: K limbs per lane, K even (coop_ops.cuh), the entry padded to 32 K limbs
+            int k = (n32 + 31) / 32;
+            k += k & 1;
+            kernel_fn cf = mdz_kernel_coop(k);
+            if (!cf) { set_err("MPFR precision %ld: no warp-per-pixel kernel for %d limbs per lane", v->precision, k); return nullptr; }
+            *n32_out = 32 * k;
+            if (coop_k_out) *coop_k_out = k;
+            return cf;
+        }
     } else if (v->mode == MDZCUDA_MODE_GMP) {
         // mpf_init2(p): precision in limbs P = (max(53,p)+127)/64, storage P+1 limbs
         const long pb = v->precision < 53 ? 53 : v->precision;
-        if (pb > 32L * 4096) { set_err("GMP precision %ld: no GPU kernel", v->precision); return nullptr; }
+        if (pb > 8192) { set_err("GMP mpf precision %ld: no GPU kernel", v->precision); return nullptr; }
         n32 = 2 * (int)((pb + 127) / 64 + 1);
     }
     else { set_err("unknown mode %d", v->mode); return nullptr; }
@@ -575,6 +594,7 @@ static int kernel_facts(int device, kernel_fn fn, int smem, int n32, mdzcuda_ker
         if (occ < 1) { set_err("kernel for %d limbs does not fit on an SM", n32); return 0; }
         mdzcuda_kernel_info ki;
         ki.limbs = n32;
+        ki.lanes_per_pixel = 1;
         ki.regs_per_thread = fa.numRegs;
         ki.local_bytes = (int)fa.localSizeBytes;
         ki.shared_bytes = smem;
@@ -604,8 +624,8 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
     if (device < 0 || device >= ndev) { set_err("device %d out of range (%d visible)", device, ndev); return nullptr; }
     if (device >= kMaxDev) { set_err("device %d: this build pools at most %d devices", device, kMaxDev); return nullptr; }
 
-    int n32 = 0;
-    kernel_fn fn = kernel_for_view(v, &n32);
+    int n32 = 0, coop_k = 0;
+    kernel_fn fn = kernel_for_view(v, &n32, &coop_k);
     if (!fn) return nullptr;
     const bool gmp = v->mode == MDZCUDA_MODE_GMP;
 
@@ -613,6 +633,7 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
     pl->view = *v;
     pl->device = device;
     pl->n32 = n32;
+    pl->coop_k = coop_k;
     pl->band_first = band_first; pl->band_stride = band_stride;
     memset(&pl->colour, 0, sizeof pl->colour);
     const int total_bands = v->real_height / v->aa_factor;
@@ -684,8 +705,11 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
         CUDA_OKP(pool_event(device, &pl->done_ev));
         CUDA_OKP(pool_pinned(device, &pl->h_pinned));                    // staging words for progress / cancel traffic
 
-        const int smem = (gmp ? gmp_smem_words(n32 / 2) : smem_words_for_limbs(n32)) * kBlock * (int)sizeof(uint32_t);   // c_re, c_im, shifter scratch, checkpoint
+        const int smem = coop_k ? mdz_smem_words_coop(coop_k) * (int)sizeof(uint32_t)                                    // one shifter strip per warp
+                                : (gmp ? gmp_smem_words(n32 / 2) : smem_words_for_limbs(n32)) * kBlock * (int)sizeof(uint32_t);   // c_re, c_im, shifter scratch, checkpoint
         if (!kernel_facts(device, fn, smem, n32, &pl->info)) goto fail;
+        pl->info.limbs = coop_k ? limbs32_for_prec(v->precision) : n32;
+        pl->info.lanes_per_pixel = coop_k ? 32 : 1;
     }
     return pl;
 fail:
@@ -852,6 +876,7 @@ static int default_chunk(int n32)
     // to a few percent of a chunk for every limb count
     if (n32 <= 2) return 32;
     if (n32 <= 4) return 16;
+    if (n32 > 32) return 4;             // one warp per pixel: an iteration is microseconds, the poll a few hundred cycles
     return 8;
 }
 
@@ -895,6 +920,7 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         p.family = pl->view.family;
         p.fractal = pl->view.fractal;
         p.chunk = pl->chunk ? pl->chunk : default_chunk(pl->n32);
+        p.prec_bits = (int)pl->view.precision;
         p.spec = pl->spec;
         if (p.spec == 1) { static const int forced = [] { const char* e = getenv("MDZCUDA_SPEC_LEVEL"); return e && *e ? atoi(e) : 1; }(); p.spec = forced; }   // A/B: 2 / 3 pin level 1 / 2
         p.colour = pl->colour;
@@ -911,8 +937,8 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         p.ld_masks.im_keep = p.fractal == FRACTAL_BURNING_SHIP ? 0u : 1u;           // ld64_step.cuh: ld64_masks
         p.ld_masks.re_and = p.fractal == FRACTAL_VARIANT ? 1u : 0u;
         p.ld_masks.re_xor = p.fractal == FRACTAL_GENERALIZED_CELTIC ? 0u : 1u;
-        const int cyc = (pl->cycle && !pl->gmp) ? 1 : 0;
-        kernel_fn fn = pl->gmp ? gmp_kernel_for_limbs(pl->n32 / 2) : kernel_for_limbs(pl->n32, cyc);
+        const int cyc = (pl->cycle && !pl->gmp && !pl->coop_k) ? 1 : 0;
+        kernel_fn fn = pl->coop_k ? mdz_kernel_coop(pl->coop_k) : pl->gmp ? gmp_kernel_for_limbs(pl->n32 / 2) : kernel_for_limbs(pl->n32, cyc);
         if (!fn) { set_err("no kernel for %d limbs", pl->n32); return 0; }
         mdzcuda_kernel_info ki;
         if (!kernel_facts(pl->device, fn, pl->info.shared_bytes, pl->n32, &ki)) return 0;
@@ -920,9 +946,11 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         if (bps > ki.blocks_per_sm) bps = ki.blocks_per_sm;
         long long npx = (long long)pl->local_lines * pl->view.real_width;
         long long grid = (long long)bps * ki.sm_count;
-        long long need = (npx + kBlock - 1) / kBlock;
+        const int px_per_block = pl->coop_k ? kBlock / 32 : kBlock;
+        long long need = (npx + px_per_block - 1) / px_per_block;
         if (grid > need) grid = need;
         ki.grid_blocks = (int)grid;
+        ki.limbs = pl->info.limbs; ki.lanes_per_pixel = pl->info.lanes_per_pixel;
         pl->info = ki;
         p.cycle = cyc;
         p.cycle_scratch = nullptr;

@@ -51,6 +51,52 @@ def test_reference_cmdline_on_libmdzcuda(name, tmp_path):
         assert np.array_equal(got_rgb, rgb)
 
 
+def wide_meta(prec, w, h, depth):
+    """gallery/test.mdz's settings (tests/golden/test_240x180.npz) at another precision, size and depth"""
+    meta, _, _ = G.load("test_240x180")
+    m = dict(meta)
+    text = meta["mdz_text"].replace("precision 80\n", "precision %d\n" % prec).replace("depth 3000\n", "depth %d\n" % depth)
+    assert text != meta["mdz_text"]
+    m.update(mdz_text=text, width=w, height=h, precision=prec, name="wide%d" % prec)
+    return m
+
+
+def test_precision_2048_file_renders_on_the_gpu(tmp_path):
+    """A `precision 2048` settings file through the unmodified reference's cmdline: the stock binary (its own
+    pthread pool) and the one linked against libmdzcuda must write the same raw_data and the same image, and the
+    drop-in must have rendered it with the CUDA kernels (no fallback line on stderr)."""
+    stock, ours = os.path.join(REF, "mdz"), os.path.join(REF, "mdz_cuda")
+    if not (os.path.exists(stock) and os.path.exists(ours)):
+        pytest.skip("oracle/_ref binaries not built")
+    meta = wide_meta(2048, 96, 72, 400)
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    want_raw, want_rgb = run_cmdline(stock, meta, tmp_path / "a")
+    got_raw, got_rgb = run_cmdline(ours, meta, tmp_path / "b")
+    assert np.array_equal(got_raw, want_raw), "%d raw pixels differ" % int((got_raw != want_raw).sum())
+    assert np.array_equal(got_rgb, want_rgb)
+
+
+def test_precision_beyond_the_kernels_falls_back_to_the_host_callback(tmp_path):
+    """`precision 16384` is a legal setting (src/image_info.c:535: 80..99999999) with no GPU kernel: the drop-in must
+    render it with MDZ's own line callback -- correct image, one line on stderr -- not report a blank one as done."""
+    stock, ours = os.path.join(REF, "mdz"), os.path.join(REF, "mdz_cuda")
+    if not (os.path.exists(stock) and os.path.exists(ours)):
+        pytest.skip("oracle/_ref binaries not built")
+    meta = wide_meta(16384, 40, 30, 200)
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    want_raw, _ = run_cmdline(stock, meta, tmp_path / "a")
+    src = tmp_path / "b" / (meta["name"] + ".mdz")
+    src.write_text(meta["mdz_text"])
+    out = tmp_path / "b" / "o.ppm"
+    r = subprocess.run([ours, "-l", str(src), "-w", "40", "-h", "30", "-A", "1", "-t", "4", "-R", str(out)],
+                       check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, cwd=str(tmp_path / "b"), timeout=600)
+    assert "no GPU kernel" in r.stderr and "host's own line callback" in r.stderr, r.stderr[-500:]
+    blob = open(str(out) + ".raw", "rb").read()
+    hdr, rest = blob.split(b"\n", 1)
+    raw = np.frombuffer(rest[:40 * 30 * 4], dtype=np.int32).reshape(30, 40)
+    assert np.array_equal(raw, want_raw)
+
+
 def test_rth_protocol(tmp_path):
     exe = str(tmp_path / "rth_protocol")
     subprocess.check_call(["gcc", "-std=gnu99", "-O1", "-o", exe,

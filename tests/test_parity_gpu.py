@@ -38,6 +38,36 @@ def test_mpfr_precisions_seahorse(ref_lib, prec):
     check(make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", 96, 72, precision=prec, depth=1500), ref_lib)
 
 
+# Above 1024 bits a pixel is rendered by a whole warp (coop_kernel.cuh: limbs split over the lanes, shuffle
+# products, ballot carries).  The reference accepts any precision from 80 bits up (src/image_info.c:535);
+# kernels are instantiated to 8192 bits.  Precisions that fill the lanes' 1024 K bits and that do not.
+@pytest.mark.parametrize("prec", [1025, 1100, 2048, 3000, 4096, 6144, 8192])
+def test_mpfr_wide_precisions_warp_per_pixel(ref_lib, prec):
+    w, h = (64, 48) if prec <= 4096 else (40, 30)
+    v = make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", w, h, precision=prec, depth=600)
+    p = mdz_b200.Plan(v, 0)
+    assert p.kernel_info()["lanes_per_pixel"] == 32 and p.kernel_info()["limbs"] == (prec + 31) // 32
+    p.close()
+    raw = check(v, ref_lib)
+    assert (raw > 0).any()
+
+
+@pytest.mark.parametrize("fractal", [MANDELBROT, BURNING_SHIP, GENERALIZED_CELTIC, VARIANT])
+def test_mpfr_2048_fractals_julia_and_antialias(ref_lib, fractal):
+    check(make_view("-0.5", "-0.3", "3.5", 64, 48, precision=2048, depth=200, fractal=fractal), ref_lib)
+    check(make_view("0", "0", "3.2", 48, 36, precision=2048, depth=150, fractal=fractal, aa=2,
+                    family=FAMILY_JULIA, julia=("-0.8", "0.156")), ref_lib)
+
+
+def test_mpfr_2048_next_to_a_minibrot(ref_lib):
+    """The orbit of every pixel returns to ~0 once per period: 200 cancelled bits in two additions, then 400-bit
+    exponent gaps (tests/views.py MINIBROT120) -- and part of the frame runs to depth."""
+    from views import MINIBROT120
+    v = make_view(MINIBROT120[0], MINIBROT120[1], "1e-120", 32, 18, precision=2048, depth=2500)
+    raw = check(v, ref_lib)
+    assert (raw == 0).any() and (raw > 0).any()
+
+
 @pytest.mark.parametrize("fractal", [MANDELBROT, BURNING_SHIP, GENERALIZED_CELTIC, VARIANT])
 @pytest.mark.parametrize("prec", [80, 128, 320])
 def test_mpfr_fractals(ref_lib, fractal, prec):
