@@ -44,7 +44,7 @@ def test_mpfr_precisions_seahorse(ref_lib, prec):
 @pytest.mark.parametrize("prec", [1025, 1100, 2048, 3000, 4096, 6144, 8192])
 def test_mpfr_wide_precisions_warp_per_pixel(ref_lib, prec):
     w, h = (64, 48) if prec <= 4096 else (40, 30)
-    v = make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", w, h, precision=prec, depth=600)
+    v = make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", w, h, precision=prec, depth=1500)
     p = mdz_b200.Plan(v, 0)
     assert p.kernel_info()["lanes_per_pixel"] == 32 and p.kernel_info()["limbs"] == (prec + 31) // 32
     p.close()
@@ -63,7 +63,7 @@ def test_mpfr_2048_next_to_a_minibrot(ref_lib):
     """The orbit of every pixel returns to ~0 once per period: 200 cancelled bits in two additions, then 400-bit
     exponent gaps (tests/views.py MINIBROT120) -- and part of the frame runs to depth."""
     from views import MINIBROT120
-    v = make_view(MINIBROT120[0], MINIBROT120[1], "1e-120", 32, 18, precision=2048, depth=2500)
+    v = make_view(MINIBROT120[0], MINIBROT120[1], "1e-120", 32, 18, precision=2048, depth=7000)
     raw = check(v, ref_lib)
     assert (raw == 0).any() and (raw > 0).any()
 
