@@ -525,10 +525,14 @@ static int prologue_gmp(const mdzcuda_view* v, const std::vector<int>& lines,
         // A host that keeps the constant as mpf (or wants another conversion) passes it directly.
         if (v->gjulia_re && v->gjulia_im) { mpf_set(x, v->gjulia_re); mpf_set(y, v->gjulia_im); }
         else {
+            // MDZCUDA_RE_FORMAT=full: the host was built with the format fixed to "%Re" (the oracle's mdz_fixre
+            // binaries), whose own my_mpfr_to_str the rth_* layer cannot reach
+            const char* e = getenv("MDZCUDA_RE_FORMAT");
+            const bool full = e && !strcmp(e, "full");
             char buf[4097];
-            mpfr_snprintf(buf, 4096, "%.Re", v->julia_re);
+            if (full) mpfr_snprintf(buf, 4096, "%Re", v->julia_re); else mpfr_snprintf(buf, 4096, "%.Re", v->julia_re);
             mpf_set_str(x, buf, 10);
-            mpfr_snprintf(buf, 4096, "%.Re", v->julia_im);
+            if (full) mpfr_snprintf(buf, 4096, "%Re", v->julia_im); else mpfr_snprintf(buf, 4096, "%.Re", v->julia_im);
             mpf_set_str(y, buf, 10);
         }
         jc.set_mpf(0, x); jc.set_mpf(1, y);

@@ -453,7 +453,11 @@ extern "C" int rth_process_lines_rendered(rthdata* rth)
         timeout.tv_sec = tv.tv_sec + ns / 1000000000L;
         timeout.tv_nsec = ns % 1000000000L;
         pthread_mutex_lock(&d->lines_rendered_mutex);
-        pthread_cond_timedwait(&d->lines_rendered_cond, &d->lines_rendered_mutex, &timeout);
+        // (Once every line is rendered no further signal can arrive, so there is nothing to wait for: the
+        // reference sleeps its 0.5 ms regardless, which makes the Julia preview's consumer -- a window of
+        // line_draw_count + 1 = 3 lines per call, image_info.c:50 -- spend 15 ms on a finished 90-line frame.)
+        if (d->total_lines_rendered < rth->img->real_height)
+            pthread_cond_timedwait(&d->lines_rendered_cond, &d->lines_rendered_mutex, &timeout);
         int unrendered = 0;
         for (int i = miny; i < maxy; ++i) {
             char* lr = &d->lines_rendered[i];

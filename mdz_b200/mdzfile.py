@@ -13,7 +13,7 @@ image_info_set resets the width to the initial 4.0 (SURVEY finding 4).
 """
 import re
 
-from .coords import center_to_rect, coords_precision, rect_to_gmp
+from .coords import mpfr_to_decimal, center_to_rect, coords_precision, rect_to_gmp
 from .mp import Mpfr, mpfr
 from .render import (ImageView, FAMILY_MANDEL, FAMILY_JULIA, MANDELBROT, BURNING_SHIP,
                      GENERALIZED_CELTIC, VARIANT)
@@ -215,6 +215,12 @@ def view_from_settings(s, width=None, height=None, aa=1, aspect_opt=0.0,
         # (c_im keeps its previous precision, image_info.c:271-272 -- 80 bits by default)
         view.julia_re = Mpfr(ip, Mpfr(P, s.julia[0]))
         view.julia_im = Mpfr(ip if not bug_compatible else 80, Mpfr(P, s.julia[1]))
+        if view.mode == 2 and fixed_re:
+            # GMP mode converts the constant to mpf through decimal text per pixel (fractal.c:341-342, coords.c:13-18);
+            # a host with the "%Re" fix hands the library the mpf values it would have got (include/mdzcuda.h: gjulia_*)
+            from .mp import Mpf
+            view.gjulia_re = Mpf(P, mpfr_to_decimal(view.julia_re, True))       # mpf_init2(c_re, img->precision), fractal.c:286
+            view.gjulia_im = Mpf(P, mpfr_to_decimal(view.julia_im, True))
     info = dict(colour_scale=s.colour_scale, palette_ip=s.palette_ip, pal_offset=s.pal_offset,
                 palette=s.palette, palette_file=s.palette_file)
     return view, info

@@ -39,6 +39,14 @@ SYNTH = [
     synthetic("celtic_mpfr128_aa2", "family mandelbrot\nfractal generalized celtic\ndepth 300\naspect 1.0\n"
               "colour-scale 1.25\ncolour-interpolate no\nmulti-precision yes\nmulti-rounding yes\nprecision 128\n"
               "cx -0.5\ncy 0.0\nsize 4.0\npalette-offset 5\n"),
+    # Julia + GMP mpf: the reference converts the constant per pixel through decimal text (fractal.c:341-342,
+    # my_mpfr_to_str.c:68), one digit with "%.Re" on MPFR 4 -- stock build -- and all digits in the "%Re" build
+    synthetic("julia_gmp128_asis", "family julia\nfractal mandelbrot\ndepth 300\naspect 1.33333333333333325932\n"
+              "colour-scale 0.8\ncolour-interpolate no\nmulti-precision yes\nmulti-rounding no\nprecision 128\n"
+              "cx 0.0\ncy 0.0\nsize 3.2\njulia-real -0.8\njulia-imag 0.156\n"),
+    synthetic("julia_gmp128_fixre", "family julia\nfractal mandelbrot\ndepth 300\naspect 1.33333333333333325932\n"
+              "colour-scale 0.8\ncolour-interpolate no\nmulti-precision yes\nmulti-rounding no\nprecision 128\n"
+              "cx 0.0\ncy 0.0\nsize 3.2\njulia-real -0.8\njulia-imag 0.156\n"),
     synthetic("julia_mpfr96", "family julia\nfractal mandel-celtic hybrid\ndepth 300\naspect 1.33333333333333325932\n"
               "colour-scale 0.8\ncolour-interpolate yes\nmulti-precision yes\nmulti-rounding yes\nprecision 96\n"
               "cx 0.0\ncy 0.0\nsize 3.2\njulia-real -0.8\njulia-imag 0.156\n"),
@@ -57,7 +65,10 @@ RUNS = [
     ("polyp", GALLERY + "/polyp.mdz", 32, 24, 2),
     ("space_pad_fixre", GALLERY + "/space_pad.mdz", 32, 32, 1),
     ("floral_fixre", GALLERY + "/floral.mdz", 32, 32, 1),
-] + [(n, None, w, h, a) for (n, _), (w, h, a) in zip(SYNTH, [(96, 54, 1), (40, 30, 3), (36, 36, 2), (48, 36, 1)])]
+    # GMP mode exactly as the stock reference behaves with this box's MPFR 4.2.1: the rect keeps one decimal digit
+    # (SURVEY finding 3) and the view collapses; the drop-in inherits that and must reproduce it
+    ("space_pad_asis", GALLERY + "/space_pad.mdz", 32, 32, 1),
+] + [(n, None, w, h, a) for (n, _), (w, h, a) in zip(SYNTH, [(96, 54, 1), (40, 30, 3), (36, 36, 2), (48, 36, 1), (48, 36, 1), (48, 36, 1)])]
 
 
 def run_one(name, src, w, h, aa, tmp):
@@ -72,7 +83,8 @@ def run_one(name, src, w, h, aa, tmp):
         src = dst
     exe = os.path.join(ROOT, "oracle", "_ref", "mdz_fixre" if name.endswith("_fixre") else "mdz")
     out = os.path.join(tmp, name + ".ppm")
-    subprocess.run([exe, "-l", src, "-w", str(w), "-h", str(h), "-A", str(aa), "-t", "8", "-R", out],
+    threads = "1" if name.startswith("julia_gmp") else "8"     # Julia + GMP converts through a static buffer shared by the workers
+    subprocess.run([exe, "-l", src, "-w", str(w), "-h", str(h), "-A", str(aa), "-t", threads, "-R", out],
                    check=True, stdout=subprocess.DEVNULL, cwd=tmp)
     blob = open(out + ".raw", "rb").read()
     hdr, rest = blob.split(b"\n", 1)

@@ -63,6 +63,7 @@ int main(int argc, char** argv)
     usleep(2000);
     rth_ui_start_render(rth);
     rth_ui_wait_until_started(rth);
+    rth_ui_stop_render_and_wait(rth);       /* callers stop a render before they touch its buffers (image_info_gui.c:397) */
     memset(img->raw_data, 0xff, sizeof(int) * W * H);
 
     /* 3: and once more from scratch, consumed to completion */

@@ -110,8 +110,11 @@ def port_render_gmp(view, threads=None):
     jre = jim = None
     if view.family == 1:
         # mpfr_to_gmp through "%.Re" (fractal.c:341-342, my_mpfr_to_str.c:68)
-        jre = C.pointer(to_mpf(Mpf(view.precision, mpfr_to_decimal(view.julia_re, False)), keep))
-        jim = C.pointer(to_mpf(Mpf(view.precision, mpfr_to_decimal(view.julia_im, False)), keep))
+        # the constant as the host's conversion leaves it: the view's own mpf copy ("%Re" hosts), else "%.Re" (stock)
+        gre = getattr(view, "gjulia_re", None) or Mpf(view.precision, mpfr_to_decimal(view.julia_re, False))
+        gim = getattr(view, "gjulia_im", None) or Mpf(view.precision, mpfr_to_decimal(view.julia_im, False))
+        jre = C.pointer(to_mpf(gre, keep))
+        jim = C.pointer(to_mpf(gim, keep))
     P = (max(53, view.precision) + 127) // 64
     out = np.full((view.real_height, view.real_width), -1, dtype=np.int32)
     ok = lib.oracle_render_gmp(P, view.family, view.fractal, view.depth, view.real_width, view.real_height,

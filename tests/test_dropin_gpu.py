@@ -23,8 +23,10 @@ def run_cmdline(exe, meta, tmp_path):
     src = tmp_path / (meta["name"] + ".mdz")
     src.write_text(meta["mdz_text"])
     out = tmp_path / (meta["name"] + ".ppm")
+    # a host built with the "%Re" fix says so: the library converts the Julia constant of GMP mode itself (include/mdzcuda.h)
+    env = dict(os.environ, MDZCUDA_RE_FORMAT="full") if meta.get("fixre") else None
     r = subprocess.run([exe, "-l", str(src), "-w", str(meta["width"]), "-h", str(meta["height"]),
-                        "-A", str(meta["aa"]), "-t", "4", "-R", str(out)],
+                        "-A", str(meta["aa"]), "-t", "4", "-R", str(out)], env=env,
                        check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, cwd=str(tmp_path), timeout=300)
     # the image has to come from the CUDA kernels, not from the host callback the drop-in keeps as its fallback
     assert "libmdzcuda" not in r.stderr, r.stderr[-1000:]

@@ -66,6 +66,20 @@ def test_config3_deep_embedded_julia_1920x1080_mpfr320(ref_lib):
     assert not bad, "%d lines differ after the two-plan render: %s" % (len(bad), bad[:40])
 
 
+def test_config3_as_is_width4_view_1920x1080_mpfr320(ref_lib):
+    """BASELINE configs[2] exactly as the reference's cmdline renders gallery/deep_embedded_julia.mdz: an old-style
+    file loses its zoom there (SURVEY finding 4), so the render is a width-4 view centred on the file's centre, at
+    the file's MPFR-320 -- SURVEY 8(d) config 3 (i).  ~2.5 G pixel-iterations, a sixth of the frame inside."""
+    import golden_util as G
+    from mdz_b200.mdzfile import view_from_settings
+    meta, _, _ = G.load("deep_embedded_julia_asis")
+    v, _ = view_from_settings(G.settings_of(meta), 1920, 1080, 1, bug_compatible=True, fixed_re=False)
+    assert v.precision == 320 and v.mode == 1
+    got = mdz_b200.render(v)
+    assert (got == 0).any() and (got > 0).any()
+    check_lines(ref_lib, v, got, sample_lines(1080, 10))
+
+
 @pytest.mark.parametrize("mode", ["gmp", "mpfr"])
 def test_config4_3840x2160_512bit_deep_zoom_with_minibrot(ref_lib, mode):
     """BASELINE configs[3] as SURVEY 8(d) specifies it: a 1e-120 wide view at 512 bits, depth 100000, on a

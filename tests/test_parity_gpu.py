@@ -319,3 +319,34 @@ def test_delivery_never_runs_ahead_of_the_kernel(ref_lib):
         q.close()
         assert np.array_equal(out[first::2], want[first::2]), rep
         assert (out[1 - first::2] == -1).all()
+
+
+def test_cycle_detection_is_invisible_on_random_views():
+    """The exact periodicity check is on behind rth_* (rth.cpp), the one place where the drop-in does different work
+    from the reference by default: a property test over random views -- every fractal, both families, long double
+    and three MPFR precisions, with and without anti-aliasing -- that raw_data is identical with it on and off."""
+    import random
+    rng = random.Random(20261017)
+    modes = [("ld", 64), ("mpfr", 96), ("mpfr", 128), ("mpfr", 256)]
+    for k in range(48):
+        mode, prec = modes[k % 4]
+        fractal = [MANDELBROT, BURNING_SHIP, GENERALIZED_CELTIC, VARIANT][(k // 4) % 4]
+        julia = rng.random() < 0.3
+        size = 10 ** rng.uniform(-2.5, 0.6)
+        # centres that keep part of the set in view: near the boundary of the main body
+        cx, cy = rng.uniform(-1.6, 0.4), rng.uniform(-0.9, 0.9)
+        kw = dict(mode=mode, precision=max(prec, 80) if mode == "ld" else prec, depth=rng.choice([300, 1000, 3000]),
+                  aa=rng.choice([1, 1, 2]), fractal=fractal)
+        if julia:
+            kw.update(family=FAMILY_JULIA, julia=("%.6f" % rng.uniform(-1.2, 0.4), "%.6f" % rng.uniform(-0.8, 0.8)))
+            cx, cy, size = rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3), 10 ** rng.uniform(-0.5, 0.5)
+        v = make_view("%.9f" % cx, "%.9f" % cy, "%.9g" % size, 80, 60, **kw)
+        a = mdz_b200.Plan(v, 0)
+        plain = a.run()
+        a.close()
+        b = mdz_b200.Plan(v, 0)
+        b.set_cycle_detection(True)
+        checked = b.run()
+        b.close()
+        assert np.array_equal(plain, checked), "view %d (%s p%d fractal %d julia %s): %d pixels differ" % (
+            k, mode, prec, fractal, julia, int((plain != checked).sum()))
