@@ -134,7 +134,9 @@ void*     mdzcuda_plan_stream(mdzcuda_plan*);
 /*
  * The sequence in which a plan's pixel queue visits its bands.  RASTER (default; what the rth_* layer uses):
  * top to bottom, the order in which the reference's pool hands lines out (src/render_threads.c:366-369), so
- * that a consumer sees the image grow from the top.  CENTRE_OUT: from the middle band outwards.  A pixel that
+ * that a consumer sees the image grow from the top.  CENTRE_OUT: from the middle of the image outwards -- a
+ * plan's bands are cut into up to 16 tiles each and the tiles taken by distance from the image centre (fed
+ * plans: whole bands, from the middle band outwards).  A pixel that
  * runs to depth occupies its lane for `depth` dependent iterations -- half a second at 512 bits and depth
  * 100000 -- and a render cannot end before the last one started has finished; deep-zoom views keep their
  * dense part (a minibrot) near the centre, so starting there takes that latency out of the tail: it is what

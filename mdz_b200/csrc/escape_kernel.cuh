@@ -54,9 +54,11 @@ __device__ __forceinline__ bool publish_bands(const EscapeParams& p, int finishe
 // The pixel queue.
 //
 // Static plans: position q of the queue is pixel q of the plan's own lines (raster order).
-// Fed plans (p.order != nullptr; several devices sharing one image, mdzcuda.cu "band scheduler"):
-// the queue runs over *slots* of one band (aa lines) each, and the host fills the slots while the
-// kernel runs -- p.order[slot] is the band it put there, p.feed[0] the number of slots filled so
+// Ordered plans (p.order != nullptr): the queue runs over *slots* of one tile each (aa lines x tile_w
+// columns; a whole band when tiles_per_band is 1) and p.order[slot] says which tile that is -- a static
+// plan that starts in the middle of the image (mdzcuda_plan_set_order), or a
+// fed plan (several devices sharing one image, mdzcuda.cu "band scheduler"), whose slots -- whole bands --
+// the host fills while the kernel runs: p.order[slot] is the band it put there, p.feed[0] the number of slots filled so
 // far, p.feed[1] == p.gen once no more will come.  A lane whose claim lies beyond the filled part
 // keeps it as a reservation (the index stays in `idx` with kReserved set) and looks again at the next
 // refill; after the close, reservations beyond the final limit are void.  The host writes order[],
@@ -77,7 +79,7 @@ __device__ __forceinline__ bool claim_pixels(const EscapeParams& p, unsigned lan
         f0 = __shfl_sync(0xffffffffu, f0, 0);
         f1 = __shfl_sync(0xffffffffu, f1, 0);
         closed = f1 == p.gen;
-        limit = f0 * ((unsigned)p.width * (unsigned)p.aa);
+        limit = f0 * ((unsigned)p.tile_w * (unsigned)p.aa);
         pending = !active && (idx & kReserved) != 0u;
         if (pending) {
             const unsigned want = idx & ~kReserved;
@@ -107,12 +109,13 @@ __device__ __forceinline__ bool claim_pixels(const EscapeParams& p, unsigned lan
 __device__ __forceinline__ void pixel_of_claim(const EscapeParams& p, unsigned idx, unsigned& pix, int& line, int& ix)
 {
     if (p.order) {
-        const unsigned band_px = (unsigned)p.width * (unsigned)p.aa;
-        const unsigned slot = idx / band_px, rem = idx - slot * band_px;
-        const unsigned band = __ldcg(&p.order[slot]);
-        const unsigned l = rem / (unsigned)p.width;
+        const unsigned tw = (unsigned)p.tile_w, slot_px = tw * (unsigned)p.aa;
+        const unsigned slot = idx / slot_px, rem = idx - slot * slot_px;
+        const unsigned code = __ldcg(&p.order[slot]);
+        const unsigned band = code / (unsigned)p.tiles_per_band, tile = code - band * (unsigned)p.tiles_per_band;
+        const unsigned l = rem / tw;
         line = (int)(band * (unsigned)p.aa + l);
-        ix = (int)(rem - l * (unsigned)p.width);
+        ix = (int)(tile * tw + rem - l * tw);
         pix = (unsigned)line * (unsigned)p.width + (unsigned)ix;
     } else {
         pix = idx;
@@ -140,7 +143,9 @@ __device__ __forceinline__ void load_entry(const CoordTable& t, int i, Num<N>& v
 
 // limb counts for which the speculative iteration (escape_step.cuh) is compiled in:
 // it keeps the previous state alive for the fall-back, 4N extra registers
-template <int N> struct SpecLimbs { static constexpr bool value = N >= 2 && N <= 16; };   // N = 2: ld64_step.cuh
+template <int N> struct SpecLimbs { static constexpr bool value = N >= 2 && N <= 10; };   // N = 2: ld64_step.cuh
+// ... and for which the hybrid iteration (escape_step.cuh pixel_step_hybrid: fall-backs inside the step, no checkpoint)
+template <int N> struct HybridLimbs { static constexpr bool value = N >= 11 && N <= 16; };
 // ... and from where on its checkpoint lives in shared memory instead of registers
 template <int N> struct SpecSmemCkpt { static constexpr bool value = N > 10 && SpecLimbs<N>::value; };
 // shared-memory words per thread: c_re, c_im, limb-shifter scratch, checkpoint
@@ -485,6 +490,8 @@ escape_mpfr_kernel(const EscapeParams p)
                 bool esc;
                 if (SpecLimbs<N>::value)
                     esc = pixel_step_auto<N, SpecSmemCkpt<N>::value>(st, cre_m, cim_m, scr, ckpt, p.rc, abs_im, abs_re, spec_level, rare_seen);
+                else if (HybridLimbs<N>::value && p.spec != 0)
+                    esc = pixel_step_hybrid<N>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re);
                 else
                     esc = pixel_step<N>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re);
                 const int iter = st.iter;
@@ -534,15 +541,19 @@ escape_mpfr_kernel(const EscapeParams p)
                     spec_level = 1;
                 }
             } else {
-                // Multi-limb kernels, two modes.  The speculative step and the general one are ~20 KB of
-                // unrolled code each and the SM's instruction cache holds 32 KB: a warp that alternates
-                // between them -- and makes its neighbours' code miss as well -- runs at half the pace of
-                // either (ncu: 7 stall cycles per issue waiting for instructions; B200, 512 bits, a view next
-                // to a minibrot, where every orbit comes back to ~0 once per period and two iterations in 707
-                // cancel 200 bits / add across a 400-bit gap: 6.8 G it/s alternating, 12.5 general only, 14.5
-                // where nothing falls back).  So a warp speculates only while fewer than one iteration in 32
-                // falls back, judged over windows of 64 iterations; otherwise it runs the general step for an
-                // exponentially growing number of chunks (16 ... 4096) before it looks again.
+                // Multi-limb kernels, two modes.  From 11 limbs up the speculative step and the general one are ~20 KB
+                // of unrolled code each and the SM's instruction cache holds 32 KB: warps that alternate between them --
+                // or run different ones side by side -- make each other's code miss (ncu: 7 stall cycles per issue
+                // waiting for instructions) and run at half the pace of either.  Measured on the B200 at 512 bits on
+                // the view next to a minibrot (every orbit comes back to ~0 once per period: two iterations in 707
+                // cancel 200 bits / add across a 400-bit gap): 6.8 G it/s with three variants in play, 12.2 with two
+                // chosen per warp at a fall-back rate of 1/32, 13.1 with the general step alone -- against 14.5 where
+                // nothing ever falls back; and one GPU's eighth of that frame took 741 ms against 620.  So there a warp
+                // leaves the speculative step at the FIRST fall-back in a window of 64 iterations, stays with the
+                // general one for at least 512 chunks (doubling to 4096 while its probes keep failing) and only a
+                // probe window without any fall-back brings it back.  Below 11 limbs both variants fit the cache and
+                // the speculative one is worth more (+25 % at 96-128 bits): a warp gives it up only above one
+                // fall-back in 32 iterations, for 16 ... 4096 chunks.
                 // (one register: spec_pause counts the window's iterations in its low half and its fall-backs in
                 // the high half while speculating, and the chunks left to sit out while not)
                 if (spec_level != 0) {
@@ -550,8 +561,9 @@ escape_mpfr_kernel(const EscapeParams p)
                     if ((spec_pause & 0xffff) >= 64) {
                         const int fell = spec_pause >> 16, steps = spec_pause & 0xffff;
                         spec_pause = 0;
-                        if (fell * 32 > steps) {
+                        if (N > 10 ? fell > 0 : fell * 32 > steps) {
                             spec_backoff = spec_backoff < 4096 ? spec_backoff * 2 : 4096;
+                            if (N > 10 && spec_backoff < 512) spec_backoff = 512;
                             spec_pause = spec_backoff;
                             spec_level = 0;
                         } else if (fell == 0) spec_backoff = 8;

@@ -59,7 +59,9 @@ struct EscapeParams {
     int park_sms;                   // SMs of the device
     // Fed plans (several devices on one image, mdzcuda.cu "band scheduler"): the queue runs over slots of
     // one band each that the host fills while the kernel runs.  nullptr: static plan, queue position = pixel.
-    const unsigned int* order;              // [slot] -> band
+    const unsigned int* order;              // [slot] -> band * tiles_per_band + tile (a tile: aa lines x tile_w columns)
+    int tile_w;                             // columns per tile (width / tiles_per_band); whole bands: width
+    int tiles_per_band;
     const volatile unsigned int* feed;      // [0] slots filled so far, [1] == gen: no more will come
     int prec_bits;          // MPFR precision in bits (the warp-per-pixel kernels derive their rounding position from it)
     Ld64Masks ld_masks;     // ld64_masks(fractal), filled in by the host so that the hot loop reads them as constants

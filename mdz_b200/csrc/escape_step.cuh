@@ -167,6 +167,68 @@ MDZ_HD bool pixel_step_spec_wide(PixelState<N>& st, const uint32_t* cre_m, const
 }
 
 
+// Hybrid iteration (11 limbs and up): the speculative operations with their fall-backs *inside* the step.
+// pixel_step_auto redoes a whole iteration with the general step when any speculative operation declines;
+// from 11 limbs up those two steps are ~20 KB of unrolled code each, the SM's instruction cache holds 32 KB,
+// and a warp that alternates between them -- or merely runs next to one that does -- waits for instructions
+// (ncu: 7 stall cycles per issue; B200, 512 bits, next to a minibrot, where every orbit returns to ~0 once per
+// period and two iterations in 707 cancel 200 bits or add across a 400-bit gap: 6.8 G it/s with the adaptive
+// levels, 13.1 with the general step alone, against 14.5 on views where nothing ever declines).  Here only the
+// part that declined is redone, in place: a product by the exact out-of-line product (probability ~N 2^-29), the
+// three additions by the general fadd (~10 KB of code).  Nothing is overwritten before it is known to be good,
+// so there is no checkpoint, no second copy of the products, no per-warp level to adapt -- and one lane's rare
+// addition costs its warp three general additions instead of an iteration and two cache refills.
+template <int N>
+MDZ_HD bool pixel_step_hybrid(PixelState<N>& st, const uint32_t* cre_m, const uint32_t* cim_m,
+                              uint32_t* scr, const RoundCfg& rc, bool abs_im, int abs_re)
+{
+    // an orbit on the real axis stays there: the general step's short form (pixel_step)
+    if (is_zero(st.wim) && cim_m[(N - 1) * kScratchStride] == 0u)
+        return pixel_step<N>(st, cre_m, cim_m, scr, rc, abs_im, abs_re);
+    ++st.iter;
+    MDZ_COUNT(CNT_ITER);
+    Num<N> t, u, c, c2, nre, nim;
+    MDZ_UNROLL
+    for (int q = 0; q < N; ++q) c.m[q] = cim_m[q * kScratchStride];
+    c.e = st.cim_e; c.s = st.cim_s;
+    MDZ_UNROLL
+    for (int q = 0; q < N; ++q) c2.m[q] = cre_m[q * kScratchStride];
+    c2.e = st.cre_e; c2.s = st.cre_s;
+    const bool drop_re = abs_re == 1 || (abs_re == 2 && (st.iter & 1));
+    uint32_t rm = 0, ra = 0;
+    fmul_spec<N>(st.wre, st.wim, t, rc, rm);
+    fadd_spec<N, MODE_SUB_POS>(st.wre2, st.wim2, u, rc, ra);
+    if (drop_re) u.s = 0;
+    fadd_spec<N, MODE_GENERIC>(u, c2, nre, rc, ra);
+    if (rm) { MDZ_COUNT(CNT_MUL_BAIL); t = fmul_general<N>(st.wre, st.wim, rc); }
+    if (t.m[N - 1] != 0) t.e += 1;
+    if (abs_im) t.s = 0;
+    fadd_spec<N, MODE_GENERIC>(t, c, nim, rc, ra);
+    if (ra) {
+        MDZ_COUNT(CNT_SPEC_FALLBACK);
+        // c is read again from its shared-memory column (through a volatile pointer, so that the compiler does not
+        // keep 2N registers alive across the fast path just for this branch)
+        const volatile uint32_t* vre = cre_m;
+        const volatile uint32_t* vim = cim_m;
+        fadd<N, MODE_SUB_POS>(st.wre2, st.wim2, u, rc, scr);
+        if (drop_re) u.s = 0;
+        MDZ_UNROLL
+        for (int q = 0; q < N; ++q) c2.m[q] = vre[q * kScratchStride];
+        fadd<N, MODE_GENERIC>(u, c2, nre, rc, scr);
+        MDZ_UNROLL
+        for (int q = 0; q < N; ++q) c.m[q] = vim[q * kScratchStride];
+        fadd<N, MODE_GENERIC>(t, c, nim, rc, scr);
+    }
+    st.wre = nre; st.wim = nim;
+    uint32_t r1 = 0, r2 = 0;
+    fsqr_spec<N>(st.wre, st.wre2, rc, r1);
+    fsqr_spec<N>(st.wim, st.wim2, rc, r2);
+    if (r1) { MDZ_COUNT(CNT_MUL_BAIL); Num<N> f = fmul_general<N>(st.wre, st.wre, rc); f.s = 0; st.wre2 = f; }
+    if (r2) { MDZ_COUNT(CNT_MUL_BAIL); Num<N> f = fmul_general<N>(st.wim, st.wim, rc); f.s = 0; st.wim2 = f; }
+    return escaped<N>(st.wim2, st.wre2, rc, scr);
+}
+
+
 // Checkpoint of the loop-carried state for the speculative step.  For small limb
 // counts it simply stays in registers; for large ones (4N extra registers would cost a
 // resident block) it goes to a per-thread shared-memory column of 4N+5 words.

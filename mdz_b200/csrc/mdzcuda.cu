@@ -22,6 +22,7 @@
 #include <map>
 
 #include <atomic>
+#include <algorithm>
 
 #include "../../include/mdzcuda.h"
 #include "escape_params.cuh"
@@ -332,6 +333,8 @@ static size_t arena_put(Arena& a, const HostTable& h, size_t& om, size_t& oe, si
 // ---------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------
+constexpr int kMaxTilesPerBand = 16;     // a band of a centre-out static plan is cut into at most this many tiles
+
 struct mdzcuda_plan {
     mdzcuda_view view;          // scalars only are used after create
     int device = 0;
@@ -364,8 +367,9 @@ struct mdzcuda_plan {
     bool gmp = false;
     // fed plan (band scheduler): queue slots filled by the host while the kernel runs
     bool fed = false;
-    int order_mode = 0;                 // MDZCUDA_ORDER_*: the sequence in which the queue visits the plan's bands
+    int order_mode = 0;                 // MDZCUDA_ORDER_*: the sequence in which the queue visits the plan's bands / tiles
     bool order_uploaded = false;
+    int tiles_per_band = 1;             // static plans in centre-out order cut their bands into this many tiles
     unsigned int* d_order = nullptr;    // [nbands] slot -> band
     unsigned int* d_feed = nullptr;     // [0] slots filled, [1] generation of the launch that is closed
     unsigned int* h_stage = nullptr;    // pinned staging: [nbands] order entries + [4] control words
@@ -669,7 +673,7 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
             const size_t o_flag = ar.reserve((size_t)pl->nbands + 1);
             const size_t o_cancel = ar.reserve(4);
             const size_t o_feed = ar.reserve(4);
-            const size_t o_order = ar.reserve((size_t)pl->nbands + 1);
+            const size_t o_order = ar.reserve((size_t)pl->nbands * kMaxTilesPerBand + 1);
             CUDA_OKP(pool_alloc(device, (void**)&pl->d_arena, ar.words * sizeof(uint32_t)));
             table_image.swap(ar.host); table_bytes = table_words * sizeof(uint32_t);
             uint32_t* b = pl->d_arena;
@@ -929,13 +933,31 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         if (p.spec == 1) { static const int forced = [] { const char* e = getenv("MDZCUDA_SPEC_LEVEL"); return e && *e ? atoi(e) : 1; }(); p.spec = forced; }   // A/B: 2 / 3 pin level 1 / 2
         p.colour = pl->colour;
         if (!pl->fed && pl->order_mode != MDZCUDA_ORDER_RASTER && !pl->order_uploaded) {
-            // a static plan that visits its bands in another sequence: the slot table, once
-            std::vector<unsigned int> seq((size_t)pl->nbands);
-            for (int k = 0; k < pl->nbands; ++k) seq[(size_t)k] = (unsigned int)band_at(pl->order_mode, pl->nbands, k);
+            // A static plan that starts in the middle of the image: its bands are cut into tiles (as many as divide
+            // the width evenly, at most 16) and the tiles sorted by their distance from the image centre, in units
+            // of the image's half extent -- the slot table, uploaded once.
+            int ntile = 1;
+            for (int t = kMaxTilesPerBand; t >= 1; --t) if (pl->view.real_width % t == 0 && pl->view.real_width / t >= 32) { ntile = t; break; }
+            pl->tiles_per_band = ntile;
+            const int total_bands = pl->view.real_height / pl->view.aa_factor;
+            std::vector<std::pair<double, unsigned int> > key((size_t)pl->nbands * ntile);
+            for (int b = 0; b < pl->nbands; ++b) {
+                const double gy = ((pl->band_first + (double)b * pl->band_stride + 0.5) / total_bands - 0.5) * 2.0;
+                for (int t = 0; t < ntile; ++t) {
+                    const double gx = ((t + 0.5) / ntile - 0.5) * 2.0;
+                    key[(size_t)b * ntile + t] = std::make_pair(gx * gx + gy * gy, (unsigned int)(b * ntile + t));
+                }
+            }
+            std::sort(key.begin(), key.end());
+            std::vector<unsigned int> seq(key.size());
+            for (size_t k = 0; k < key.size(); ++k) seq[k] = key[k].second;
             CUDA_OK(cudaMemcpyAsync(pl->d_order, seq.data(), seq.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, pl->side));
             CUDA_OK(cudaStreamSynchronize(pl->side));
             pl->order_uploaded = true;
         }
+        if (pl->fed || pl->order_mode == MDZCUDA_ORDER_RASTER) pl->tiles_per_band = 1;
+        p.tiles_per_band = pl->tiles_per_band;
+        p.tile_w = pl->view.real_width / pl->tiles_per_band;
         p.order = (pl->fed || pl->order_mode != MDZCUDA_ORDER_RASTER) ? pl->d_order : nullptr;
         p.feed = pl->fed ? (const volatile unsigned int*)pl->d_feed : nullptr;
         p.ld_masks.im_keep = p.fractal == FRACTAL_BURNING_SHIP ? 0u : 1u;           // ld64_step.cuh: ld64_masks

@@ -107,6 +107,11 @@ static long pixel(long prec, int fractal, long depth, int spec,
     const int abs_re = fractal == FRACTAL_GENERALIZED_CELTIC ? 1 : fractal == FRACTAL_VARIANT ? 2 : 0;
     uint32_t rare_seen = 0;
     uint32_t ck[CkptWords<N>::value];
+    if (spec == 5) {            // the hybrid iteration (fall-backs inside the step), the kernels' choice from 11 limbs up
+        while (st.iter < depth)
+            if (pixel_step_hybrid<N>(st, cre, cim, scr, rc, abs_im, abs_re)) return st.iter;
+        return 0;
+    }
     while (st.iter < depth)
         if ((spec == 2 || spec == 4) ? pixel_step_auto<N, true>(st, cre, cim, scr, ck, rc, abs_im, abs_re, spec == 4 ? 2 : 1, rare_seen)
                                      : pixel_step_auto<N, false>(st, cre, cim, scr, ck, rc, abs_im, abs_re, spec == 3 ? 2 : spec, rare_seen)) return st.iter;

@@ -33,7 +33,7 @@ def test_long_double_fractals(ref_lib, fractal):
     check(make_view("-0.5", "-0.3", "3.5", 160, 120, mode="ld", depth=500, fractal=fractal), ref_lib)
 
 
-@pytest.mark.parametrize("prec", [80, 96, 128, 176, 184, 256, 320, 512, 544, 640, 800, 1024])
+@pytest.mark.parametrize("prec", [80, 96, 128, 176, 184, 256, 320, 352, 384, 416, 448, 480, 512, 544, 640, 800, 1024])
 def test_mpfr_precisions_seahorse(ref_lib, prec):
     check(make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", 96, 72, precision=prec, depth=1500), ref_lib)
 
@@ -350,3 +350,20 @@ def test_cycle_detection_is_invisible_on_random_views():
         b.close()
         assert np.array_equal(plain, checked), "view %d (%s p%d fractal %d julia %s): %d pixels differ" % (
             k, mode, prec, fractal, julia, int((plain != checked).sum()))
+
+
+@pytest.mark.parametrize("w,h,aa,first,stride", [(320, 200, 1, 0, 1), (50, 37, 3, 0, 1), (384, 216, 2, 1, 3), (3840, 40, 1, 0, 1), (97, 61, 1, 2, 5)])
+def test_centre_out_order_changes_nothing(w, h, aa, first, stride):
+    """mdzcuda_plan_set_order: the queue takes the plan's bands cut into tiles, by distance from the image centre,
+    instead of in raster order.  Scheduling only -- raw_data must be the same, for whole images, for one rank's
+    interleaved share, for widths no tile count divides."""
+    v = make_view("-0.6", "0.1", "2.8", w, h, precision=96, depth=400, aa=aa)
+    a = mdz_b200.Plan(v, 0, first, stride)
+    plain = a.run()
+    a.close()
+    b = mdz_b200.Plan(v, 0, first, stride)
+    b.set_order(centre_out=True)
+    ordered = b.run()
+    again = b.run()          # the same plan launched twice keeps its table
+    b.close()
+    assert np.array_equal(plain, ordered) and np.array_equal(plain, again)

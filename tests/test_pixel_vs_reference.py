@@ -9,7 +9,7 @@ import pytest
 
 from mdz_b200 import MANDELBROT, BURNING_SHIP, GENERALIZED_CELTIC, VARIANT
 from mdz_b200.mp import Mpfr, MpfrStruct, mpfr, nlimbs64
-from views import make_view, deep_embedded_julia, honeytrace, SEAHORSE
+from views import make_view, deep_embedded_julia, honeytrace, SEAHORSE, MINIBROT120
 
 U = C.POINTER(C.c_uint64)
 P = C.POINTER(MpfrStruct)
@@ -74,12 +74,17 @@ CASES = [
     ("real axis ship p64", lambda: make_view("-0.5", "0.0", "3.5", 64, 48, precision=64, depth=500, fractal=BURNING_SHIP), 64),
     ("real axis celtic p128", lambda: make_view("-0.5", "0.0", "3.5", 64, 48, precision=128, depth=500, fractal=GENERALIZED_CELTIC), 64),
     ("real axis hybrid p320", lambda: make_view("-0.5", "0.0", "3.5", 64, 48, precision=320, depth=500, fractal=VARIANT), 64),
+    # next to the period-707 minibrot every orbit returns to ~0 once per period: 200 cancelled bits, then 400-bit gaps
+    ("minibrot p512", lambda: make_view(MINIBROT120[0], MINIBROT120[1], "1e-120", 64, 36, precision=512, depth=2200), 6),
+    ("minibrot p448 ship", lambda: make_view(MINIBROT120[0], MINIBROT120[1], "1e-120", 64, 36, precision=448, depth=1500, fractal=BURNING_SHIP), 6),
+    ("seahorse p384 celtic", lambda: make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", 96, 72, precision=384, depth=600, fractal=GENERALIZED_CELTIC), 16),
+    ("seahorse p352 hybrid", lambda: make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", 96, 72, precision=352, depth=600, fractal=VARIANT), 16),
 ]
 
 
 @pytest.mark.parametrize("name,mk,count", CASES, ids=[c[0] for c in CASES])
-@pytest.mark.parametrize("spec", [0, 1, 2, 3, 4], ids=["general", "speculative", "speculative-smem-checkpoint",
-                                                  "speculative-wide", "speculative-wide-smem-checkpoint"])
+@pytest.mark.parametrize("spec", [0, 1, 2, 3, 4, 5], ids=["general", "speculative", "speculative-smem-checkpoint",
+                                                     "speculative-wide", "speculative-wide-smem-checkpoint", "hybrid"])
 def test_pixels_match_reference(emu, ref_lib, name, mk, count, spec):
     view = mk()
     W, H = view.real_width, view.real_height
@@ -101,7 +106,7 @@ def test_real_axis_shortcut_matches_reference(emu, ref_lib, fractal, prec):
                "0.25", "0.2500001", "0.3", "1", "2", "-2.0000001"):
         x = Mpfr(prec, xs)
         want = ref_pixel(ref_lib, view, x, zero)
-        for spec in (0, 1, 3):
+        for spec in (0, 1, 3, 5):
             assert emu_pixel(emu, view, x, zero, spec) == want, (fractal, prec, xs, spec)
 
 
