@@ -143,9 +143,16 @@ __device__ __forceinline__ void load_entry(const CoordTable& t, int i, Num<N>& v
 
 // limb counts for which the speculative iteration (escape_step.cuh) is compiled in:
 // it keeps the previous state alive for the fall-back, 4N extra registers
-template <int N> struct SpecLimbs { static constexpr bool value = N >= 2 && N <= 10; };   // N = 2: ld64_step.cuh
+#ifndef MDZ_HYBRID_MIN
+#define MDZ_HYBRID_MIN 11       // smallest limb count that runs the hybrid iteration (A/B builds: make EXTRA=-DMDZ_HYBRID_MIN=3)
+#endif
+template <int N> struct SpecLimbs { static constexpr bool value = N >= 2 && N < (N == 2 ? 3 : MDZ_HYBRID_MIN); };   // N = 2: ld64_step.cuh
 // ... and for which the hybrid iteration (escape_step.cuh pixel_step_hybrid: fall-backs inside the step, no checkpoint)
-template <int N> struct HybridLimbs { static constexpr bool value = N >= 11 && N <= 16; };
+template <int N> struct HybridLimbs { static constexpr bool value = N >= MDZ_HYBRID_MIN && N <= 16 && N > 2; };
+// From 11 limbs up the hybrid iteration is the only one a warp runs (a second, general copy of the unrolled step next
+// to it is what the instruction cache cannot hold, and the adaptive machinery alone cost 3 % at 512 bits); below that
+// -- A/B builds -- a warp may give it up for the general step when most of its iterations decline.
+template <int N> struct HybridAdapts { static constexpr bool value = HybridLimbs<N>::value && N <= 10; };
 // ... and from where on its checkpoint lives in shared memory instead of registers
 template <int N> struct SpecSmemCkpt { static constexpr bool value = N > 10 && SpecLimbs<N>::value; };
 // shared-memory words per thread: c_re, c_im, limb-shifter scratch, checkpoint
@@ -382,7 +389,7 @@ escape_mpfr_kernel(const EscapeParams p)
     CycleState cyc; cyc.f0 = 0; cyc.f1 = 0; cyc.next = 0x7fffffff;
     // warp-uniform: 0 general step, 1 speculative, 2 (long double mode only) speculative with the level-2 additions
     // (p.spec: 0 off, 1 adaptive; 2 / 3 pin level 1 / 2 for A/B measurements)
-    int spec_level = (SpecLimbs<N>::value && p.spec != 0) ? (p.spec == 3 ? 2 : 1) : 0;
+    int spec_level = ((SpecLimbs<N>::value || HybridLimbs<N>::value) && p.spec != 0) ? (p.spec == 3 && N == 2 ? 2 : 1) : 0;
     int spec_pause = 0, spec_backoff = 8;
     unsigned pix = 0;
 
@@ -490,8 +497,8 @@ escape_mpfr_kernel(const EscapeParams p)
                 bool esc;
                 if (SpecLimbs<N>::value)
                     esc = pixel_step_auto<N, SpecSmemCkpt<N>::value>(st, cre_m, cim_m, scr, ckpt, p.rc, abs_im, abs_re, spec_level, rare_seen);
-                else if (HybridLimbs<N>::value && p.spec != 0)
-                    esc = pixel_step_hybrid<N>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re);
+                else if (HybridLimbs<N>::value && spec_level != 0)
+                    esc = pixel_step_hybrid<N>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re, rare_seen);
                 else
                     esc = pixel_step<N>(st, cre_m, cim_m, scr, p.rc, abs_im, abs_re);
                 const int iter = st.iter;
@@ -510,7 +517,7 @@ escape_mpfr_kernel(const EscapeParams p)
                 }
             }
             // one lane falling back makes the whole warp wait for the general step
-            if (SpecLimbs<N>::value && spec_level != 0) {
+            if ((SpecLimbs<N>::value || HybridAdapts<N>::value) && spec_level != 0) {
                 warp_steps += 1;
                 warp_fell += __any_sync(0xffffffffu, rare_seen != rare_before) ? 1 : 0;
             }
@@ -522,7 +529,7 @@ escape_mpfr_kernel(const EscapeParams p)
         // ---- adapt: speculation is only worth it while fall-backs are scarce ----
         // One lane that falls back makes its whole warp run the general step as well, and an event that a
         // lane meets once in three hundred iterations a warp of unsynchronised lanes meets in every tenth.
-        if (SpecLimbs<N>::value && p.spec == 1) {
+        if ((SpecLimbs<N>::value || HybridAdapts<N>::value) && p.spec == 1) {
             if constexpr (N == 2) {
                 // Long double mode, three levels (ld64_step.cuh): when more than a quarter of a chunk's
                 // iterations had a fall-back, level 1 gives way to level 2 (far smaller or zero second
@@ -541,19 +548,13 @@ escape_mpfr_kernel(const EscapeParams p)
                     spec_level = 1;
                 }
             } else {
-                // Multi-limb kernels, two modes.  From 11 limbs up the speculative step and the general one are ~20 KB
-                // of unrolled code each and the SM's instruction cache holds 32 KB: warps that alternate between them --
-                // or run different ones side by side -- make each other's code miss (ncu: 7 stall cycles per issue
-                // waiting for instructions) and run at half the pace of either.  Measured on the B200 at 512 bits on
-                // the view next to a minibrot (every orbit comes back to ~0 once per period: two iterations in 707
-                // cancel 200 bits / add across a 400-bit gap): 6.8 G it/s with three variants in play, 12.2 with two
-                // chosen per warp at a fall-back rate of 1/32, 13.1 with the general step alone -- against 14.5 where
-                // nothing ever falls back; and one GPU's eighth of that frame took 741 ms against 620.  So there a warp
-                // leaves the speculative step at the FIRST fall-back in a window of 64 iterations, stays with the
-                // general one for at least 512 chunks (doubling to 4096 while its probes keep failing) and only a
-                // probe window without any fall-back brings it back.  Below 11 limbs both variants fit the cache and
-                // the speculative one is worth more (+25 % at 96-128 bits): a warp gives it up only above one
-                // fall-back in 32 iterations, for 16 ... 4096 chunks.
+                // Multi-limb kernels, two modes: the hybrid iteration (escape_step.cuh pixel_step_hybrid: speculative
+                // additions, redone with the general fadd when one declines) or the general step.  Trying costs the
+                // speculative additions (~6N instructions each against ~10N), so it pays while fewer than about a third
+                // of a warp's iterations decline; judged over windows of 64 iterations, the general step then stays for
+                // an exponentially growing number of chunks (16 ... 4096) before the warp tries again.  (Kernels built
+                // with the older whole-iteration fall-back, pixel_step_auto -- A/B builds with MDZ_HYBRID_MIN above the
+                // limb count -- pay a full general step per fall-back and give up at 1/32.)
                 // (one register: spec_pause counts the window's iterations in its low half and its fall-backs in
                 // the high half while speculating, and the chunks left to sit out while not)
                 if (spec_level != 0) {
@@ -561,9 +562,8 @@ escape_mpfr_kernel(const EscapeParams p)
                     if ((spec_pause & 0xffff) >= 64) {
                         const int fell = spec_pause >> 16, steps = spec_pause & 0xffff;
                         spec_pause = 0;
-                        if (N > 10 ? fell > 0 : fell * 32 > steps) {
+                        if (HybridLimbs<N>::value ? fell * 3 > steps : fell * 32 > steps) {
                             spec_backoff = spec_backoff < 4096 ? spec_backoff * 2 : 4096;
-                            if (N > 10 && spec_backoff < 512) spec_backoff = 512;
                             spec_pause = spec_backoff;
                             spec_level = 0;
                         } else if (fell == 0) spec_backoff = 8;

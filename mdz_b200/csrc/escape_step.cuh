@@ -178,9 +178,12 @@ MDZ_HD bool pixel_step_spec_wide(PixelState<N>& st, const uint32_t* cre_m, const
 // three additions by the general fadd (~10 KB of code).  Nothing is overwritten before it is known to be good,
 // so there is no checkpoint, no second copy of the products, no per-warp level to adapt -- and one lane's rare
 // addition costs its warp three general additions instead of an iteration and two cache refills.
+// rare_seen counts the iterations in which the speculative additions had to be redone: a warp whose orbits make
+// them decline most of the time (gallery/deep_embedded_julia.mdz: wre^2 - wim^2 has a 31..40-bit exponent gap in
+// every second iteration) is better off with the general step from the start; escape_kernel.cuh "adapt" decides.
 template <int N>
 MDZ_HD bool pixel_step_hybrid(PixelState<N>& st, const uint32_t* cre_m, const uint32_t* cim_m,
-                              uint32_t* scr, const RoundCfg& rc, bool abs_im, int abs_re)
+                              uint32_t* scr, const RoundCfg& rc, bool abs_im, int abs_re, uint32_t& rare_seen)
 {
     // an orbit on the real axis stays there: the general step's short form (pixel_step)
     if (is_zero(st.wim) && cim_m[(N - 1) * kScratchStride] == 0u)
@@ -205,6 +208,7 @@ MDZ_HD bool pixel_step_hybrid(PixelState<N>& st, const uint32_t* cre_m, const ui
     if (abs_im) t.s = 0;
     fadd_spec<N, MODE_GENERIC>(t, c, nim, rc, ra);
     if (ra) {
+        rare_seen += 1u;
         MDZ_COUNT(CNT_SPEC_FALLBACK);
         // c is read again from its shared-memory column (through a volatile pointer, so that the compiler does not
         // keep 2N registers alive across the fast path just for this branch)

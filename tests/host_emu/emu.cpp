@@ -109,7 +109,7 @@ static long pixel(long prec, int fractal, long depth, int spec,
     uint32_t ck[CkptWords<N>::value];
     if (spec == 5) {            // the hybrid iteration (fall-backs inside the step), the kernels' choice from 11 limbs up
         while (st.iter < depth)
-            if (pixel_step_hybrid<N>(st, cre, cim, scr, rc, abs_im, abs_re)) return st.iter;
+            if (pixel_step_hybrid<N>(st, cre, cim, scr, rc, abs_im, abs_re, rare_seen)) return st.iter;
         return 0;
     }
     while (st.iter < depth)
