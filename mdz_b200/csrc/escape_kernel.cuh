@@ -389,7 +389,7 @@ escape_mpfr_kernel(const EscapeParams p)
     CycleState cyc; cyc.f0 = 0; cyc.f1 = 0; cyc.next = 0x7fffffff;
     // warp-uniform: 0 general step, 1 speculative, 2 (long double mode only) speculative with the level-2 additions
     // (p.spec: 0 off, 1 adaptive; 2 / 3 pin level 1 / 2 for A/B measurements)
-    int spec_level = ((SpecLimbs<N>::value || HybridLimbs<N>::value) && p.spec != 0) ? (p.spec == 3 && N == 2 ? 2 : 1) : 0;
+    int spec_level = ((SpecLimbs<N>::value || HybridLimbs<N>::value) && p.spec != 0) ? (p.spec == 3 ? 2 : 1) : 0;
     int spec_pause = 0, spec_backoff = 8;
     unsigned pix = 0;
 
