@@ -190,40 +190,40 @@ MDZ_HD bool pixel_step_hybrid(PixelState<N>& st, const uint32_t* cre_m, const ui
         return pixel_step<N>(st, cre_m, cim_m, scr, rc, abs_im, abs_re);
     ++st.iter;
     MDZ_COUNT(CNT_ITER);
-    Num<N> t, u, c, c2, nre, nim;
-    MDZ_UNROLL
-    for (int q = 0; q < N; ++q) c.m[q] = cim_m[q * kScratchStride];
-    c.e = st.cim_e; c.s = st.cim_s;
-    MDZ_UNROLL
-    for (int q = 0; q < N; ++q) c2.m[q] = cre_m[q * kScratchStride];
-    c2.e = st.cre_e; c2.s = st.cre_s;
+    Num<N> t, u, c;
     const bool drop_re = abs_re == 1 || (abs_re == 2 && (st.iter & 1));
+    // the product first, settled before anything else: wre and wim are dead after it, which is what keeps the
+    // 16-limb kernel's additions in registers (with the check further down ptxas spilled 31 registers per iteration)
     uint32_t rm = 0, ra = 0;
     fmul_spec<N>(st.wre, st.wim, t, rc, rm);
-    fadd_spec<N, MODE_SUB_POS>(st.wre2, st.wim2, u, rc, ra);
-    if (drop_re) u.s = 0;
-    fadd_spec<N, MODE_GENERIC>(u, c2, nre, rc, ra);
     if (rm) { MDZ_COUNT(CNT_MUL_BAIL); t = fmul_general<N>(st.wre, st.wim, rc); }
     if (t.m[N - 1] != 0) t.e += 1;
     if (abs_im) t.s = 0;
-    fadd_spec<N, MODE_GENERIC>(t, c, nim, rc, ra);
+    // the additions write straight into wre / wim: what the fall-back needs (wre2, wim2, t, c) is still intact
+    fadd_spec<N, MODE_SUB_POS>(st.wre2, st.wim2, u, rc, ra);
+    if (drop_re) u.s = 0;
+    MDZ_UNROLL
+    for (int q = 0; q < N; ++q) c.m[q] = cre_m[q * kScratchStride];
+    c.e = st.cre_e; c.s = st.cre_s;
+    fadd_spec<N, MODE_GENERIC>(u, c, st.wre, rc, ra);
+    MDZ_UNROLL
+    for (int q = 0; q < N; ++q) c.m[q] = cim_m[q * kScratchStride];
+    c.e = st.cim_e; c.s = st.cim_s;
+    fadd_spec<N, MODE_GENERIC>(t, c, st.wim, rc, ra);
     if (ra) {
         rare_seen += 1u;
         MDZ_COUNT(CNT_SPEC_FALLBACK);
-        // c is read again from its shared-memory column (through a volatile pointer, so that the compiler does not
-        // keep 2N registers alive across the fast path just for this branch)
-        const volatile uint32_t* vre = cre_m;
-        const volatile uint32_t* vim = cim_m;
         fadd<N, MODE_SUB_POS>(st.wre2, st.wim2, u, rc, scr);
         if (drop_re) u.s = 0;
         MDZ_UNROLL
-        for (int q = 0; q < N; ++q) c2.m[q] = vre[q * kScratchStride];
-        fadd<N, MODE_GENERIC>(u, c2, nre, rc, scr);
+        for (int q = 0; q < N; ++q) c.m[q] = cre_m[q * kScratchStride];
+        c.e = st.cre_e; c.s = st.cre_s;
+        fadd<N, MODE_GENERIC>(u, c, st.wre, rc, scr);
         MDZ_UNROLL
-        for (int q = 0; q < N; ++q) c.m[q] = vim[q * kScratchStride];
-        fadd<N, MODE_GENERIC>(t, c, nim, rc, scr);
+        for (int q = 0; q < N; ++q) c.m[q] = cim_m[q * kScratchStride];
+        c.e = st.cim_e; c.s = st.cim_s;
+        fadd<N, MODE_GENERIC>(t, c, st.wim, rc, scr);
     }
-    st.wre = nre; st.wim = nim;
     uint32_t r1 = 0, r2 = 0;
     fsqr_spec<N>(st.wre, st.wre2, rc, r1);
     fsqr_spec<N>(st.wim, st.wim2, rc, r2);

@@ -39,3 +39,13 @@ for p in (128, 192, 256, 320, 384, 448, 512):
     st = spills.get(("g", ki["limbs"]), ("?", "?", "?"))
     print("| GMP mpf | %d | %d | %d | %s | %s / %s | %d | %d | %d |" % (p, ki["limbs"], ki["regs_per_thread"], st[0], st[1], st[2],
                                                                     ki["shared_bytes"], ki["blocks_per_sm"], ki["blocks_per_sm"] * 4))
+for p in (2048, 4096, 6144, 8192):
+    v = make_view("-0.5", "0", "3", 32, 24, mode="mpfr", precision=p, depth=10)
+    plan = mdz_b200.Plan(v, 0)
+    plan.launch(); plan.wait()
+    ki = plan.kernel_info()
+    plan.close()
+    m = re.search(r"Compiling entry function '_ZN3mdz18escape_coop_kernelILi%dEE.*?\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads" % ((ki["limbs"] + 31) // 32 + ((ki["limbs"] + 31) // 32) % 2), rep)
+    st = m.groups() if m else ("?", "?", "?")
+    print("| MPFR, one warp per pixel | %d | %d | %d | %s | %s / %s | %d | %d | %d |" % (p, ki["limbs"], ki["regs_per_thread"], st[0], st[1], st[2],
+                                                                                     ki["shared_bytes"], ki["blocks_per_sm"], ki["blocks_per_sm"] * 4))
