@@ -244,9 +244,9 @@ def side_precisions(torch, device, peak, peak32, skip=()):
         ("mpfr80", sea(1920, 1080, precision=80)),
         ("mpfr128", sea(1920, 1080, precision=128)),
         ("mpfr320", deep_embedded_julia(1920, 1080)),
-        ("mpfr512", sea(960, 540, precision=512)),
-        ("gmp512", sea(960, 540, mode="gmp", precision=512)),
-        ("mpfr1024", sea(480, 270, precision=1024)),
+        ("mpfr512", sea(1920, 1080, precision=512)),
+        ("gmp512", sea(1920, 1080, mode="gmp", precision=512)),
+        ("mpfr1024", sea(960, 540, precision=1024)),
         ("mpfr2048", sea(240, 135, precision=2048)),
         ("mpfr4096", sea(160, 90, precision=4096)),
     ]
