@@ -161,8 +161,11 @@ template <int N> struct SmemWords {
 };
 
 // resident blocks per SM the register allocator is asked to make room for
+#ifndef MDZ_MINBLOCKS_13_16
+#define MDZ_MINBLOCKS_13_16 4       // 128 registers, 16 warps per SM: +1 ... +4 % over 3 blocks of 168 (A/B: make EXTRA=-DMDZ_MINBLOCKS_13_16=3)
+#endif
 template <int N> struct MinBlocks {
-    static constexpr int value = N <= 2 ? 6 : N <= 3 ? 8 : N <= 5 ? 6 : N <= 8 ? 5 : N <= 12 ? 4 : N <= 16 ? 3 : N <= 24 ? 2 : 1;
+    static constexpr int value = N <= 2 ? 6 : N <= 3 ? 8 : N <= 5 ? 6 : N <= 8 ? 5 : N <= 12 ? 4 : N <= 16 ? MDZ_MINBLOCKS_13_16 : N <= 24 ? 2 : 1;
 };
 
 // ---------------------------------------------------------------------------
@@ -660,7 +663,9 @@ escape_gmp_kernel(const EscapeParams p)
 // Shared memory per thread: c_re, c_im (2*NW) + shifter column (3*NW).
 // ---------------------------------------------------------------------------
 template <int NW> struct GSmemWords { static constexpr int value = 2 * NW + GScratchWords<NW>::value; };
-template <int NW> struct GMinBlocks { static constexpr int value = NW <= 8 ? 6 : NW <= 12 ? 4 : 3; };
+// (measured on the B200: 14 words -- 320 bits -- 15.1 -> 16.4 G it/s with 4 blocks of 128 registers instead of 3 of 168;
+// 20 words -- 512 bits -- 8.9 -> 8.0, the spills outweigh the fourth block)
+template <int NW> struct GMinBlocks { static constexpr int value = NW <= 8 ? 6 : NW <= 14 ? 4 : 3; };
 
 template <int NW>
 __device__ __forceinline__ void load_gf_entry(const CoordTable& t, int i, GF<NW>& v)

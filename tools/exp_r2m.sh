@@ -1,0 +1,9 @@
+run() { echo "== $*"; python tools/run_case.py "$@" | cut -c1-62; }
+for lib in "" exp/libv4.so; do
+  export MDZCUDA_LIB=$lib; echo "#### lib=${lib:-product}"
+  run mini --scale 2 --order 1
+  run misi --scale 2
+  run mpfr512 --scale 2
+  run sea448 --scale 2
+  run sea416 --scale 2
+done
