@@ -374,7 +374,8 @@ struct mdzcuda_plan {
     unsigned int* d_feed = nullptr;     // [0] slots filled, [1] generation of the launch that is closed
     unsigned int* h_stage = nullptr;    // pinned staging: [nbands] order entries + [4] control words
     size_t h_stage_cap = 0;
-    int granted = 0;                    // slots filled so far in the current launch
+    int granted = 0;                    // bands fed so far in the current launch
+    int granted_slots = 0;              // ... as queue slots (bands x tiles_per_band)
     bool closed = false;
     unsigned int claimed = 0;           // queue counter as of the last poll
     cudaStream_t own = nullptr;         // the plan's own non-blocking launch stream (mdzcuda_plan_stream)
@@ -750,6 +751,13 @@ static inline int band_at(int mode, int n, int pos)
     return b;
 }
 
+// tiles a band is cut into in centre-out order: as many as divide the width evenly, at most 16, at least 32 columns each
+static int tiles_for_width(int width)
+{
+    for (int t = kMaxTilesPerBand; t >= 1; --t) if (width % t == 0 && width / t >= 32) return t;
+    return 1;
+}
+
 extern "C" int mdzcuda_plan_set_order(mdzcuda_plan* pl, int mode)
 {
     if (!pl) { set_err("null plan"); return 0; }
@@ -766,7 +774,7 @@ extern "C" int mdzcuda_plan_set_fed(mdzcuda_plan* pl, int on)
     if (on && !pl->h_stage) {
         void* q = nullptr; size_t cap = 0;
         CUDA_OK(cudaSetDevice(pl->device));
-        CUDA_OK(pool_pinned_buf(pl->device, &q, &cap, ((size_t)pl->nbands + 8) * sizeof(unsigned int)));
+        CUDA_OK(pool_pinned_buf(pl->device, &q, &cap, ((size_t)pl->nbands * kMaxTilesPerBand + 8) * sizeof(unsigned int)));
         pl->h_stage = (unsigned int*)q; pl->h_stage_cap = cap;
     }
     pl->fed = on != 0;
@@ -781,17 +789,26 @@ extern "C" int mdzcuda_plan_feed(mdzcuda_plan* pl, const int* bands, int count, 
     if (count < 0 || pl->granted + count > pl->nbands) { set_err("feed: more bands than the plan has"); return 0; }
     if (pl->closed) { if (count == 0) return 1; set_err("feed: the launch is closed"); return 0; }
     CUDA_OK(cudaSetDevice(pl->device));
-    unsigned int* ctl = pl->h_stage + pl->nbands;
+    // The staging buffer holds the slot table (nbands x tiles_per_band entries at most) and, behind it, the control words.
+    unsigned int* ctl = pl->h_stage + (size_t)pl->nbands * kMaxTilesPerBand;
     if (count > 0) {
-        for (int k = 0; k < count; ++k) {
+        // A chunk of bands becomes `tiles_per_band` runs of slots: the chunk's tiles column by column, the columns
+        // nearest the middle of the image first (centre-out plans; one tile per band otherwise), so that what is
+        // dense in the chunk -- deep zooms keep it in the middle -- is started first (mdzcuda_plan_set_order).
+        const int nt = pl->tiles_per_band;
+        unsigned int* dst = pl->h_stage + pl->granted_slots;
+        for (int k = 0; k < count; ++k)
             if (bands[k] < 0 || bands[k] >= pl->nbands) { set_err("feed: band %d out of range", bands[k]); return 0; }
-            pl->h_stage[pl->granted + k] = (unsigned int)bands[k];
+        for (int c = 0; c < nt; ++c) {
+            const int t = band_at(MDZCUDA_ORDER_CENTRE_OUT, nt, c);      // column c of the sequence: middle outwards
+            for (int k = 0; k < count; ++k) *dst++ = (unsigned int)(bands[k] * nt + t);
         }
         // order[] first, then the limit, then the close word: the kernel reads them in the opposite order
-        CUDA_OK(cudaMemcpyAsync(pl->d_order + pl->granted, pl->h_stage + pl->granted, (size_t)count * sizeof(unsigned int),
+        CUDA_OK(cudaMemcpyAsync(pl->d_order + pl->granted_slots, pl->h_stage + pl->granted_slots, (size_t)count * nt * sizeof(unsigned int),
                                 cudaMemcpyHostToDevice, pl->side));
         pl->granted += count;
-        ctl[0] = (unsigned int)pl->granted;
+        pl->granted_slots += count * nt;
+        ctl[0] = (unsigned int)pl->granted_slots;
         CUDA_OK(cudaMemcpyAsync(pl->d_feed + 0, ctl + 0, sizeof(unsigned int), cudaMemcpyHostToDevice, pl->side));
     }
     if (close) {
@@ -898,7 +915,8 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
     if (pl->fed) {
         // the fill count restarts at zero; on the side stream, where the feeds will follow it in order
         // (the close word carries the launch generation and needs no reset)
-        pl->granted = 0; pl->closed = false;
+        pl->granted = 0; pl->granted_slots = 0; pl->closed = false;
+        pl->tiles_per_band = pl->order_mode == MDZCUDA_ORDER_CENTRE_OUT ? tiles_for_width(pl->view.real_width) : 1;
         CUDA_OK(cudaMemsetAsync(pl->d_feed, 0, sizeof(unsigned int), pl->side));
         CUDA_OK(cudaStreamSynchronize(pl->side));
     }
@@ -936,8 +954,7 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
             // A static plan that starts in the middle of the image: its bands are cut into tiles (as many as divide
             // the width evenly, at most 16) and the tiles sorted by their distance from the image centre, in units
             // of the image's half extent -- the slot table, uploaded once.
-            int ntile = 1;
-            for (int t = kMaxTilesPerBand; t >= 1; --t) if (pl->view.real_width % t == 0 && pl->view.real_width / t >= 32) { ntile = t; break; }
+            const int ntile = tiles_for_width(pl->view.real_width);
             pl->tiles_per_band = ntile;
             const int total_bands = pl->view.real_height / pl->view.aa_factor;
             std::vector<std::pair<double, unsigned int> > key((size_t)pl->nbands * ntile);
@@ -955,7 +972,7 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
             CUDA_OK(cudaStreamSynchronize(pl->side));
             pl->order_uploaded = true;
         }
-        if (pl->fed || pl->order_mode == MDZCUDA_ORDER_RASTER) pl->tiles_per_band = 1;
+        if (!pl->fed && pl->order_mode == MDZCUDA_ORDER_RASTER) pl->tiles_per_band = 1;
         p.tiles_per_band = pl->tiles_per_band;
         p.tile_w = pl->view.real_width / pl->tiles_per_band;
         p.order = (pl->fed || pl->order_mode != MDZCUDA_ORDER_RASTER) ? pl->d_order : nullptr;
@@ -1335,7 +1352,7 @@ int mdz_run_view(const mdzcuda_view* view, int32_t* raw_host, const int* devices
     }
     if (ok && hooks && hooks->cycle_detection >= 0)
         for (int i = 0; i < ndev; ++i) mdzcuda_plan_set_cycle_detection(plans[i], hooks->cycle_detection);
-    if (ok && hooks && !dynamic)
+    if (ok && hooks)
         for (int i = 0; i < ndev; ++i) mdzcuda_plan_set_order(plans[i], hooks->order);
     for (int i = 0; ok && i < ndev; ++i) ok = mdzcuda_plan_launch(plans[i], plans[i]->own);
     int rc = 0;

@@ -20,13 +20,16 @@ def ndev():
     return mdz_b200.device_count()
 
 
-def test_fed_plan_single_device():
+@pytest.mark.parametrize("centre_out", [False, True], ids=["raster", "centre_out_tiles"])
+def test_fed_plan_single_device(centre_out):
     """A fed plan on ONE device, driven by hand: bands fed out of order, in several steps, while the kernel
-    runs; the result must equal the plain plan's, and the bands must arrive where they belong."""
+    runs; the result must equal the plain plan's, and the bands must arrive where they belong.  In centre-out
+    order every fed chunk is cut into tiles and its middle columns go first."""
     import ctypes as C
     v = make_view(SEAHORSE[0], SEAHORSE[1], "1e-6", 320, 200, precision=128, depth=3000)
     want = mdz_b200.render(v, (0,))
     p = mdz_b200.Plan(v, 0)
+    p.set_order(centre_out)
     assert N.lib.mdzcuda_plan_set_fed(p.h, 1)
     p.launch()
     order = list(range(199, -1, -1))            # bottom to top
