@@ -534,6 +534,11 @@ def main():
                          "unit": "T 32x32->64 MAC/s", "frac": kernel_rate * macs / peak,
                          "peak_imad32": peak32 / 1e12, "frac_of_imad32_issue": kernel_rate * macs / peak32,
                          "traffic": dram,
+                         "traffic_note": None if dram is None else
+                             "dram__bytes_read + dram__bytes_write of ONE launch of this kernel in the committed ncu --set full capture "
+                             "(profiles/r2_ncu_summary.json: %s), which renders the bench view at 960x540 -- 1/16 of the bench frame's pixels: "
+                             "algorithmic bytes of that launch are 2.07 MB of raw_data out + 0.1 MB of tables in; the results still sit in "
+                             "L2 when the kernel ends, hence less than that reaches DRAM.  Static figure, not measured in this run" % kernel_key,
                          "binding_pipe": None if not prof else {
                              "static": True, "source": "profiles/r2_ncu_summary.json: " + kernel_key,
                              "captured_at_rev": (meta or {}).get("rev"),

@@ -164,8 +164,12 @@ template <int N> struct SmemWords {
 #ifndef MDZ_MINBLOCKS_13_16
 #define MDZ_MINBLOCKS_13_16 4       // 128 registers, 16 warps per SM: +1 ... +4 % over 3 blocks of 168 (A/B: make EXTRA=-DMDZ_MINBLOCKS_13_16=3)
 #endif
+#ifndef MDZ_MINBLOCKS_BUMP
+#define MDZ_MINBLOCKS_BUMP 0        // A/B builds: one more resident block for 5..12 limbs
+#endif
 template <int N> struct MinBlocks {
-    static constexpr int value = N <= 2 ? 6 : N <= 3 ? 8 : N <= 5 ? 6 : N <= 8 ? 5 : N <= 12 ? 4 : N <= 16 ? MDZ_MINBLOCKS_13_16 : N <= 24 ? 2 : 1;
+    static constexpr int value = N <= 2 ? 6 : N <= 3 ? 8 : N <= 4 ? 6 : N <= 5 ? 6 + MDZ_MINBLOCKS_BUMP : N <= 8 ? 5 + MDZ_MINBLOCKS_BUMP
+                               : N <= 12 ? 4 + MDZ_MINBLOCKS_BUMP : N <= 16 ? MDZ_MINBLOCKS_13_16 : N <= 24 ? 2 : 1;
 };
 
 // ---------------------------------------------------------------------------

@@ -200,6 +200,7 @@ MDZ_HD bool pixel_step_hybrid(PixelState<N>& st, const uint32_t* cre_m, const ui
     if (t.m[N - 1] != 0) t.e += 1;
     if (abs_im) t.s = 0;
     // the additions write straight into wre / wim: what the fall-back needs (wre2, wim2, t, c) is still intact
+    // (forming this difference before the product, to overlap with it, measured 2.7 % slower at 16 limbs: more spills)
     fadd_spec<N, MODE_SUB_POS>(st.wre2, st.wim2, u, rc, ra);
     if (drop_re) u.s = 0;
     MDZ_UNROLL
