@@ -162,7 +162,11 @@ template <int N> struct SmemWords {
 
 // resident blocks per SM the register allocator is asked to make room for
 #ifndef MDZ_MINBLOCKS_13_16
-#define MDZ_MINBLOCKS_13_16 4       // 128 registers, 16 warps per SM: +1 ... +4 % over 3 blocks of 168 (A/B: make EXTRA=-DMDZ_MINBLOCKS_13_16=3)
+// 3 blocks of 168 registers.  4 blocks of 128 (make EXTRA=-DMDZ_MINBLOCKS_13_16=4) measured +1 ... +4 % on one GPU at 512 bits
+// (13.66 -> 14.05 G it/s on the target frame) but a pixel that runs to depth then shares its scheduler with a fourth warp:
+// 100 000 iterations take 0.54 s instead of 0.45, and the same frame split over eight GPUs went from 600 to 652 ms (99.6 ->
+// 89 % of eight times one GPU).  Latency of the deep pixels is what bounds strong scaling, so the lower occupancy stays.
+#define MDZ_MINBLOCKS_13_16 3
 #endif
 #ifndef MDZ_MINBLOCKS_BUMP
 #define MDZ_MINBLOCKS_BUMP 0        // A/B builds: one more resident block for 5..12 limbs
