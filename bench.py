@@ -247,8 +247,10 @@ def side_precisions(torch, device, peak, peak32, skip=()):
         ("mpfr512", sea(1920, 1080, precision=512)),
         ("gmp512", sea(1920, 1080, mode="gmp", precision=512)),
         ("mpfr1024", sea(960, 540, precision=1024)),
-        ("mpfr2048", sea(240, 135, precision=2048)),
-        ("mpfr4096", sea(160, 90, precision=4096)),
+        # 16 / 32 lanes per pixel: a few thousand pixels in flight, so the views hold at least forty times that
+        ("mpfr2048", sea(480, 270, precision=2048)),
+        ("mpfr4096", sea(320, 180, precision=4096)),
+        ("mpfr8192", sea(240, 135, precision=8192)),
     ]
     stream = torch.cuda.current_stream().cuda_stream
     for name, view in cases:

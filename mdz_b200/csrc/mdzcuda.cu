@@ -339,7 +339,7 @@ struct mdzcuda_plan {
     mdzcuda_view view;          // scalars only are used after create
     int device = 0;
     int n32 = 0;                // limbs per table entry (for the warp-per-pixel kernels: padded to 32 * coop_k)
-    int coop_k = 0;             // 0: one thread per pixel; K: one warp per pixel, K limbs per lane (coop_kernel.cuh)
+    int coop_k = 0;             // 0: one thread per pixel; else K * 100 + T: T lanes per pixel, K limbs per lane (coop_kernel.cuh)
     int band_first = 0, band_stride = 1, nbands = 0, local_lines = 0;
     std::vector<int> line_map;  // local line -> global line
     DevTable xs, ys, jc;
@@ -392,8 +392,9 @@ typedef void (*kernel_fn)(const EscapeParams);
 // build parallelises: one unrolled kernel per limb count is seconds to minutes of ptxas.
 kernel_fn mdz_kernel_mpfr(int n32, int cyc);    // N = 2..32 words, without / with the periodicity check (kernels_mpfr_*.cu)
 int       mdz_smem_words_mpfr(int n32);
-kernel_fn mdz_kernel_coop(int k);               // K = 2, 4, 6, 8 limbs per lane: 2048 ... 8192 bits  (kernels_coop.cu)
-int       mdz_smem_words_coop(int k);
+void      mdz_coop_shape(int n32, int* k, int* t);     // T lanes x K limbs per value for 33 .. 256 limbs  (kernels_coop.cu)
+kernel_fn mdz_kernel_coop(int k, int t);
+int       mdz_smem_words_coop(int k, int t);
 kernel_fn mdz_kernel_gmp_clear(int nl);         // NL = 3..10 limbs  (kernels_gmp.cu)
 kernel_fn mdz_kernel_gmp_fast(int nl);          // NL = 4..10 limbs  (kernels_gmpf_*.cu)
 int       mdz_smem_words_gmp_fast(int nl);
@@ -427,13 +428,13 @@ static kernel_fn kernel_for_view(const mdzcuda_view* v, int* n32_out, int* coop_
         if (v->precision > kMaxMpfrBits) { set_err("MPFR precision %ld: no GPU kernel above %d bits", v->precision, kMaxMpfrBits); return nullptr; }
         n32 = limbs32_for_prec(v->precision);
         if (n32 > 32) {
-            // one warp per pixel: K limbs per lane, K even (coop_ops.cuh), the entry padded to 32 K limbs
-            int k = (n32 + 31) / 32;
-            k += k & 1;
-            kernel_fn cf = mdz_kernel_coop(k);
-            if (!cf) { set_err("MPFR precision %ld: no warp-per-pixel kernel for %d limbs per lane", v->precision, k); return nullptr; }
-            *n32_out = 32 * k;
-            if (coop_k_out) *coop_k_out = k;
+            // a group of T lanes per pixel, K limbs per lane (coop_ops.cuh), the entry padded to T K limbs
+            int k = 0, t = 0;
+            mdz_coop_shape(n32, &k, &t);
+            kernel_fn cf = mdz_kernel_coop(k, t);
+            if (!cf) { set_err("MPFR precision %ld: no lane-group kernel for %d x %d limbs", v->precision, t, k); return nullptr; }
+            *n32_out = t * k;
+            if (coop_k_out) *coop_k_out = k * 100 + t;
             return cf;
         }
     } else if (v->mode == MDZCUDA_MODE_GMP) {
@@ -714,11 +715,11 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
         CUDA_OKP(pool_event(device, &pl->done_ev));
         CUDA_OKP(pool_pinned(device, &pl->h_pinned));                    // staging words for progress / cancel traffic
 
-        const int smem = coop_k ? mdz_smem_words_coop(coop_k) * (int)sizeof(uint32_t)                                    // one shifter strip per warp
+        const int smem = coop_k ? mdz_smem_words_coop(coop_k / 100, coop_k % 100) * (int)sizeof(uint32_t)                // one shifter strip per group
                                 : (gmp ? gmp_smem_words(n32 / 2) : smem_words_for_limbs(n32)) * kBlock * (int)sizeof(uint32_t);   // c_re, c_im, shifter scratch, checkpoint
         if (!kernel_facts(device, fn, smem, n32, &pl->info)) goto fail;
         pl->info.limbs = coop_k ? limbs32_for_prec(v->precision) : n32;
-        pl->info.lanes_per_pixel = coop_k ? 32 : 1;
+        pl->info.lanes_per_pixel = coop_k ? coop_k % 100 : 1;
     }
     return pl;
 fail:
@@ -981,7 +982,7 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         p.ld_masks.re_and = p.fractal == FRACTAL_VARIANT ? 1u : 0u;
         p.ld_masks.re_xor = p.fractal == FRACTAL_GENERALIZED_CELTIC ? 0u : 1u;
         const int cyc = (pl->cycle && !pl->gmp && !pl->coop_k) ? 1 : 0;
-        kernel_fn fn = pl->coop_k ? mdz_kernel_coop(pl->coop_k) : pl->gmp ? gmp_kernel_for_limbs(pl->n32 / 2) : kernel_for_limbs(pl->n32, cyc);
+        kernel_fn fn = pl->coop_k ? mdz_kernel_coop(pl->coop_k / 100, pl->coop_k % 100) : pl->gmp ? gmp_kernel_for_limbs(pl->n32 / 2) : kernel_for_limbs(pl->n32, cyc);
         if (!fn) { set_err("no kernel for %d limbs", pl->n32); return 0; }
         mdzcuda_kernel_info ki;
         if (!kernel_facts(pl->device, fn, pl->info.shared_bytes, pl->n32, &ki)) return 0;
@@ -989,7 +990,7 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         if (bps > ki.blocks_per_sm) bps = ki.blocks_per_sm;
         long long npx = (long long)pl->local_lines * pl->view.real_width;
         long long grid = (long long)bps * ki.sm_count;
-        const int px_per_block = pl->coop_k ? kBlock / 32 : kBlock;
+        const int px_per_block = pl->coop_k ? kBlock / (pl->coop_k % 100) : kBlock;
         long long need = (npx + px_per_block - 1) / px_per_block;
         if (grid > need) grid = need;
         ki.grid_blocks = (int)grid;

@@ -18,8 +18,10 @@ from test_pixel_vs_reference import coords, ref_pixel
 from views import make_view, SEAHORSE, MINIBROT120
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-# (lanes hold K limbs each: 32 K limbs = 1024 K bits of working width), precisions that fill it and that do not
-CASES = [(2, 2048), (2, 1025), (2, 1100), (2, 2047), (2, 1984), (4, 4096), (4, 2049), (4, 3000), (6, 6144), (6, 5000), (8, 8192), (8, 7000)]
+# (K limbs per lane, T lanes per value: T K limbs = 32 T K bits of working width), precisions that fill it and that do not;
+# 16 x 4, 16 x 8, 32 x 6, 32 x 8 are what the kernels use, the others exercise the same code at other shapes
+CASES = [(4, 16, 2048), (4, 16, 1025), (4, 16, 1100), (4, 16, 2047), (4, 16, 1984), (8, 16, 4096), (8, 16, 2049), (8, 16, 3000),
+         (6, 32, 6144), (6, 32, 5000), (8, 32, 8192), (8, 32, 7000), (2, 32, 2048), (4, 32, 4096), (2, 16, 1024), (2, 16, 700)]
 
 
 @pytest.fixture(scope="module")
@@ -30,21 +32,23 @@ def coop():
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out, src])
     lib = C.CDLL(out)
-    lib.coop_binop.argtypes = [C.c_int, C.c_int, C.c_long, U64P, C.c_int, C.c_long, U64P, C.c_int, C.c_long, U64P,
+    lib.coop_binop.argtypes = [C.c_int, C.c_int, C.c_int, C.c_long, U64P, C.c_int, C.c_long, U64P, C.c_int, C.c_long, U64P,
                                C.POINTER(C.c_int), C.POINTER(C.c_long)]
     lib.coop_pixel.restype = C.c_long
-    lib.coop_pixel.argtypes = [C.c_int, C.c_long, C.c_int, C.c_long] + [U64P, C.c_int, C.c_long] * 4
+    lib.coop_pixel.argtypes = [C.c_int, C.c_int, C.c_long, C.c_int, C.c_long] + [U64P, C.c_int, C.c_long] * 4
     return lib
 
 
-def coop_op(lib, K, op, prec, a, b):
+def coop_op(lib, KT, op, prec, a, b):
+    K, T = KT
     n = nlimbs64(prec)
     al, bl = (C.c_uint64 * n)(*a.limbs()), (C.c_uint64 * n)(*b.limbs())
     rl, rs, re_ = (C.c_uint64 * n)(), C.c_int(), C.c_long()
     sa, ea, _ = a.parts()
     sb, eb, _ = b.parts()
-    assert lib.coop_binop(K, op, prec, al, sa, ea, bl, sb, eb, rl, C.byref(rs), C.byref(re_))
+    assert lib.coop_binop(K, T, op, prec, al, sa, ea, bl, sb, eb, rl, C.byref(rs), C.byref(re_))
     assert rs.value != 99, "bits below the precision are set"
+    assert rs.value != 98, "the groups of the warp disagree"
     if op in (6, 11):
         return rs.value
     if rs.value == 0:
@@ -55,10 +59,11 @@ def coop_op(lib, K, op, prec, a, b):
     return (rs.value, re_.value, full >> (64 * n - prec))
 
 
-@pytest.mark.parametrize("K,prec", CASES)
-def test_ops_match_libmpfr(coop, K, prec):
-    rng = random.Random(5000 + prec)
-    for _ in range(400 if K <= 4 else 200):
+@pytest.mark.parametrize("K,T,prec", CASES)
+def test_ops_match_libmpfr(coop, K, T, prec):
+    rng = random.Random(5000 + prec + T)
+    K = (K, T)
+    for _ in range(400 if K[0] * T <= 128 else 200):
         a, b = rand_pair(rng, prec)
         for op, name in ((0, "mul"), (1, "sqr"), (2, "add"), (3, "sub")):
             assert coop_op(coop, K, op, prec, a, b) == mpfr_op(name, prec, a, b), (name, a.parts(), b.parts())
@@ -70,7 +75,7 @@ def test_ops_match_libmpfr(coop, K, prec):
             assert coop_op(coop, K, op, prec, a2, b2) == mpfr_op(name, prec, a2, b2), (name, a2.parts(), b2.parts())
 
 
-@pytest.mark.parametrize("K,prec", [(2, 2048), (2, 1100), (4, 4096)])
+@pytest.mark.parametrize("K,prec", [((4, 16), 2048), ((4, 16), 1100), ((8, 16), 4096), ((2, 32), 2048)])
 def test_structured_carries_across_lanes(coop, K, prec):
     """Operands that make carries / borrows run through many lanes: all-ones runs, single low bits, sums that
     wrap to a power of two, differences that cancel down to one bit."""
@@ -89,7 +94,7 @@ def test_structured_carries_across_lanes(coop, K, prec):
 
 
 def test_greater_than_4_and_escape(coop):
-    K, prec = 2, 2048
+    K, prec = (4, 16), 2048
     four = Mpfr(prec, 4)
     rng = random.Random(7)
     for _ in range(400):
@@ -110,21 +115,22 @@ def test_greater_than_4_and_escape(coop):
         assert coop_op(coop, K, 11, prec, a2, b) == (1 if mpfr.mpfr_greater_p(s.ref, four.ref) else 0)
 
 
-def coop_pixel(lib, K, view, x, y):
+def coop_pixel(lib, KT, view, x, y):
+    K, T = KT
     n = nlimbs64(view.precision)
     args = []
     for v in (x, y, x, y):
         s, e, _ = v.parts()
         args += [(C.c_uint64 * n)(*v.limbs()), s, e]
-    return lib.coop_pixel(K, view.precision, view.fractal, view.depth, *args)
+    return lib.coop_pixel(K, T, view.precision, view.fractal, view.depth, *args)
 
 
-@pytest.mark.parametrize("K,prec", [(2, 2048), (2, 1100), (4, 4096)])
+@pytest.mark.parametrize("K,prec", [((4, 16), 2048), ((4, 16), 1100), ((8, 16), 4096), ((6, 32), 6144)])
 @pytest.mark.parametrize("fractal", [MANDELBROT, BURNING_SHIP, GENERALIZED_CELTIC, VARIANT])
 def test_pixels_match_reference(coop, ref_lib, K, prec, fractal):
-    views = [make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", 64, 36, precision=prec, depth=400 if K == 2 else 150, fractal=fractal),
+    views = [make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", 64, 36, precision=prec, depth=400 if prec <= 2048 else 150, fractal=fractal),
              make_view("-0.5", "0.0", "4.0", 64, 36, precision=prec, depth=120, fractal=fractal)]
-    if fractal == MANDELBROT and K == 2:
+    if fractal == MANDELBROT and prec == 2048:
         # next to the period-707 minibrot: the orbit returns to ~0 (200 cancelled bits, then 400-bit gaps)
         views.append(make_view(MINIBROT120[0], MINIBROT120[1], "1e-120", 64, 36, precision=prec, depth=1500))
     for view in views:

@@ -38,15 +38,15 @@ def test_mpfr_precisions_seahorse(ref_lib, prec):
     check(make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", 96, 72, precision=prec, depth=1500), ref_lib)
 
 
-# Above 1024 bits a pixel is rendered by a whole warp (coop_kernel.cuh: limbs split over the lanes, shuffle
-# products, ballot carries).  The reference accepts any precision from 80 bits up (src/image_info.c:535);
+# Above 1024 bits a pixel is rendered by a group of 16 or 32 lanes (coop_kernel.cuh: limbs split over the lanes,
+# shuffle products, ballot carries).  The reference accepts any precision from 80 bits up (src/image_info.c:535);
 # kernels are instantiated to 8192 bits.  Precisions that fill the lanes' 1024 K bits and that do not.
 @pytest.mark.parametrize("prec", [1025, 1100, 2048, 3000, 4096, 6144, 8192])
 def test_mpfr_wide_precisions_warp_per_pixel(ref_lib, prec):
     w, h = (64, 48) if prec <= 4096 else (40, 30)
     v = make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", w, h, precision=prec, depth=1500)
     p = mdz_b200.Plan(v, 0)
-    assert p.kernel_info()["lanes_per_pixel"] == 32 and p.kernel_info()["limbs"] == (prec + 31) // 32
+    assert p.kernel_info()["lanes_per_pixel"] == (16 if prec <= 4096 else 32) and p.kernel_info()["limbs"] == (prec + 31) // 32
     p.close()
     raw = check(v, ref_lib)
     assert (raw > 0).any()

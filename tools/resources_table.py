@@ -45,7 +45,8 @@ for p in (2048, 4096, 6144, 8192):
     plan.launch(); plan.wait()
     ki = plan.kernel_info()
     plan.close()
-    m = re.search(r"Compiling entry function '_ZN3mdz18escape_coop_kernelILi%dEE.*?\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads" % ((ki["limbs"] + 31) // 32 + ((ki["limbs"] + 31) // 32) % 2), rep)
+    kk, tt = {2048: (4, 16), 4096: (8, 16), 6144: (6, 32), 8192: (8, 32)}[p]
+    m = re.search(r"Compiling entry function '_ZN3mdz18escape_coop_kernelILi%dELi%dEE.*?\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads" % (kk, tt), rep)
     st = m.groups() if m else ("?", "?", "?")
-    print("| MPFR, one warp per pixel | %d | %d | %d | %s | %s / %s | %d | %d | %d |" % (p, ki["limbs"], ki["regs_per_thread"], st[0], st[1], st[2],
+    print("| MPFR, %d lanes per pixel |" % ki["lanes_per_pixel"] + " %d | %d | %d | %s | %s / %s | %d | %d | %d |" % (p, ki["limbs"], ki["regs_per_thread"], st[0], st[1], st[2],
                                                                                      ki["shared_bytes"], ki["blocks_per_sm"], ki["blocks_per_sm"] * 4))
