@@ -4,10 +4,13 @@
 // 6144 and 8192.  Same pixel queue, band completion, cancel word and fed-plan protocol as the one-thread-per-pixel
 // kernels (escape_kernel.cuh); a group claims one pixel at a time.  Restates the reference's frac_*_mpfr loops
 // (src/frac_mandel.c:25-52, src/frac_burning_ship.c:27-55, src/frac_generalized_celtic.c:27-55,
-// src/frac_variant.c:26-55) and the per-pixel set-up of fractal_mpfr_calculate_line (src/fractal.c:183-203).
+// src/frac_variant.c:26-55) and the per-pixel set-up of fractal_mpfr_calculate_line (src/fractal.c:183-203); with
+// GMP = true the frac_*_gmp loops (src/frac_mandel.c:55-82 ...) and fractal_gmp_calculate_line (src/fractal.c:310-342)
+// on coop_mpf.cuh's arithmetic, for mpf precisions above 512 bits.
 #pragma once
 #include "escape_kernel.cuh"
 #include "coop_ops.cuh"
+#include "coop_mpf.cuh"
 
 namespace mdz {
 
@@ -26,7 +29,7 @@ __device__ __forceinline__ void load_coop_entry(const CoordTable& t, int i, CNum
     v.s = __ldg(&t.s[i]);
 }
 
-template <int K, int T>
+template <int K, int T, bool GMP>
 __global__ void __launch_bounds__(kBlock, CoopMinBlocks<K, T>::value)
 escape_coop_kernel(const EscapeParams p)
 {
@@ -37,9 +40,10 @@ escape_coop_kernel(const EscapeParams p)
     const unsigned lane = threadIdx.x & 31u;
     const bool leader = (threadIdx.x & (unsigned)(T - 1)) == 0u;
     const unsigned total = (unsigned)p.width * (unsigned)p.lines;
-    CoopCfg cfg;
+    CoopCfg cfg;                     // MPFR: prec_bits is the precision
     cfg.prec = p.prec_bits;
     cfg.R = 32 * T * K - p.prec_bits;
+    const CoopGCfg gcfg = make_coop_gcfg<K, T>(GMP ? p.prec_bits : 1);      // GMP: prec_bits carries NL = P + 1 limbs
     const bool abs_im = p.fractal == FRACTAL_BURNING_SHIP;
     const int  abs_re = p.fractal == FRACTAL_GENERALIZED_CELTIC ? 1
                       : p.fractal == FRACTAL_VARIANT ? 2 : 0;
@@ -73,21 +77,26 @@ escape_coop_kernel(const EscapeParams p)
                 CNum<K, T> x, y;
                 load_coop_entry<K, T>(p.xs, ix, x);
                 load_coop_entry<K, T>(p.ys, line, y);
+                if (GMP) { cg_adopt<K, T>(x); cg_adopt<K, T>(y); }
                 if (p.family == FAMILY_JULIA) {
                     CNum<K, T> cx, cy;
                     load_coop_entry<K, T>(p.jc, 0, cx);
                     load_coop_entry<K, T>(p.jc, 1, cy);
+                    if (GMP) { cg_adopt<K, T>(cx); cg_adopt<K, T>(cy); }
                     cpixel_load<K, T>(st, x, y, cx, cy);
                 } else cpixel_load<K, T>(st, x, y, x, y);
                 active = true;
             }
             __syncwarp();
-            if (__any_sync(0xffffffffu, start)) cpixel_squares<K, T>(st, cfg);     // products are the whole warp's
+            if (__any_sync(0xffffffffu, start)) {                                   // products are the whole warp's
+                if (GMP) cgpixel_squares<K, T>(st, gcfg); else cpixel_squares<K, T>(st, cfg);
+            }
             if (!__any_sync(0xffffffffu, active)) { if (queue_idle_wait(p, pix)) continue; break; }
         }
         for (int k = 0; k < p.chunk; ++k) {
             {
-                const bool esc = cpixel_step<K, T>(st, cfg, scr, abs_im, abs_re, active);
+                const bool esc = GMP ? cgpixel_step<K, T>(st, gcfg, scr, abs_im, abs_re, active)
+                                     : cpixel_step<K, T>(st, cfg, scr, abs_im, abs_re, active);
                 if (active && (esc || st.iter >= p.depth)) {
                     if (leader) {
                         p.raw[pix] = esc ? st.iter : 0;

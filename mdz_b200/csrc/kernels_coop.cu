@@ -13,10 +13,10 @@ void mdz_coop_shape(int n32, int* k, int* t)
 kernel_fn mdz_kernel_coop(int k, int t)
 {
     switch (k * 100 + t) {
-    case 416: return escape_coop_kernel<4, 16>;
-    case 816: return escape_coop_kernel<8, 16>;
-    case 632: return escape_coop_kernel<6, 32>;
-    case 832: return escape_coop_kernel<8, 32>;
+    case 416: return escape_coop_kernel<4, 16, false>;
+    case 816: return escape_coop_kernel<8, 16, false>;
+    case 632: return escape_coop_kernel<6, 32, false>;
+    case 832: return escape_coop_kernel<8, 32, false>;
     default: return nullptr;
     }
 }

@@ -394,6 +394,7 @@ kernel_fn mdz_kernel_mpfr(int n32, int cyc);    // N = 2..32 words, without / wi
 int       mdz_smem_words_mpfr(int n32);
 void      mdz_coop_shape(int n32, int* k, int* t);     // T lanes x K limbs per value for 33 .. 256 limbs  (kernels_coop.cu)
 kernel_fn mdz_kernel_coop(int k, int t);
+kernel_fn mdz_kernel_coop_gmp(int k, int t);                // GMP mpf above 512 bits  (kernels_coop_gmp.cu)
 int       mdz_smem_words_coop(int k, int t);
 kernel_fn mdz_kernel_gmp_clear(int nl);         // NL = 3..10 limbs  (kernels_gmp.cu)
 kernel_fn mdz_kernel_gmp_fast(int nl);          // NL = 4..10 limbs  (kernels_gmpf_*.cu)
@@ -418,6 +419,7 @@ static int smem_words_for_limbs(int n) { return mdz_smem_words_mpfr(n); }
 
 // the kernel that renders this mode / precision (nullptr + error text: none is instantiated)
 constexpr long kMaxMpfrBits = 8192;
+constexpr long kMaxGmpBits = 8000;      // P = (p + 127) / 64 limbs of precision, P + 2 limbs of 128 in the widest lane-group shape
 static kernel_fn kernel_for_view(const mdzcuda_view* v, int* n32_out, int* coop_k_out = nullptr)
 {
     int n32;
@@ -440,8 +442,19 @@ static kernel_fn kernel_for_view(const mdzcuda_view* v, int* n32_out, int* coop_
     } else if (v->mode == MDZCUDA_MODE_GMP) {
         // mpf_init2(p): precision in limbs P = (max(53,p)+127)/64, storage P+1 limbs
         const long pb = v->precision < 53 ? 53 : v->precision;
-        if (pb > 8192) { set_err("GMP mpf precision %ld: no GPU kernel", v->precision); return nullptr; }
-        n32 = 2 * (int)((pb + 127) / 64 + 1);
+        if (pb > kMaxGmpBits) { set_err("GMP mpf precision %ld: no GPU kernel above %ld bits", v->precision, kMaxGmpBits); return nullptr; }
+        const int nl = (int)((pb + 127) / 64 + 1);
+        n32 = 2 * nl;
+        if (!gmp_kernel_for_limbs(nl)) {
+            // a group of T lanes per pixel (coop_mpf.cuh): the NL limbs top aligned in T K words with one limb to spare
+            int k = 0, t = 0;
+            mdz_coop_shape(2 * (nl + 1), &k, &t);
+            kernel_fn cf = (2 * (nl + 1) <= t * k) ? mdz_kernel_coop_gmp(k, t) : nullptr;
+            if (!cf) { set_err("GMP mpf precision %ld: no lane-group kernel for %d limbs", v->precision, nl); return nullptr; }
+            *n32_out = t * k;
+            if (coop_k_out) *coop_k_out = k * 100 + t;
+            return cf;
+        }
     }
     else { set_err("unknown mode %d", v->mode); return nullptr; }
     kernel_fn fn = v->mode == MDZCUDA_MODE_GMP ? gmp_kernel_for_limbs(n32 / 2) : kernel_for_limbs(n32);
@@ -718,7 +731,7 @@ extern "C" mdzcuda_plan* mdzcuda_plan_create(const mdzcuda_view* v, int device,
         const int smem = coop_k ? mdz_smem_words_coop(coop_k / 100, coop_k % 100) * (int)sizeof(uint32_t)                // one shifter strip per group
                                 : (gmp ? gmp_smem_words(n32 / 2) : smem_words_for_limbs(n32)) * kBlock * (int)sizeof(uint32_t);   // c_re, c_im, shifter scratch, checkpoint
         if (!kernel_facts(device, fn, smem, n32, &pl->info)) goto fail;
-        pl->info.limbs = coop_k ? limbs32_for_prec(v->precision) : n32;
+        pl->info.limbs = !coop_k ? n32 : gmp ? 2 * (int)(((v->precision < 53 ? 53 : v->precision) + 127) / 64 + 1) : limbs32_for_prec(v->precision);
         pl->info.lanes_per_pixel = coop_k ? coop_k % 100 : 1;
     }
     return pl;
@@ -948,6 +961,7 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         p.fractal = pl->view.fractal;
         p.chunk = pl->chunk ? pl->chunk : default_chunk(pl->n32);
         p.prec_bits = (int)pl->view.precision;
+        if (pl->gmp && pl->coop_k) p.prec_bits = (int)(((pl->view.precision < 53 ? 53 : pl->view.precision) + 127) / 64 + 1);  // NL = P + 1 limbs (coop_mpf.cuh)
         p.spec = pl->spec;
         if (p.spec == 1) { static const int forced = [] { const char* e = getenv("MDZCUDA_SPEC_LEVEL"); return e && *e ? atoi(e) : 1; }(); p.spec = forced; }   // A/B: 2 / 3 pin level 1 / 2
         p.colour = pl->colour;
@@ -982,7 +996,7 @@ extern "C" int mdzcuda_plan_launch(mdzcuda_plan* pl, void* cuda_stream)
         p.ld_masks.re_and = p.fractal == FRACTAL_VARIANT ? 1u : 0u;
         p.ld_masks.re_xor = p.fractal == FRACTAL_GENERALIZED_CELTIC ? 0u : 1u;
         const int cyc = (pl->cycle && !pl->gmp && !pl->coop_k) ? 1 : 0;
-        kernel_fn fn = pl->coop_k ? mdz_kernel_coop(pl->coop_k / 100, pl->coop_k % 100) : pl->gmp ? gmp_kernel_for_limbs(pl->n32 / 2) : kernel_for_limbs(pl->n32, cyc);
+        kernel_fn fn = pl->coop_k ? (pl->gmp ? mdz_kernel_coop_gmp : mdz_kernel_coop)(pl->coop_k / 100, pl->coop_k % 100) : pl->gmp ? gmp_kernel_for_limbs(pl->n32 / 2) : kernel_for_limbs(pl->n32, cyc);
         if (!fn) { set_err("no kernel for %d limbs", pl->n32); return 0; }
         mdzcuda_kernel_info ki;
         if (!kernel_facts(pl->device, fn, pl->info.shared_bytes, pl->n32, &ki)) return 0;

@@ -9,7 +9,7 @@ import pytest
 import mdz_b200
 from mdz_b200 import (FAMILY_JULIA, MANDELBROT, BURNING_SHIP, GENERALIZED_CELTIC, VARIANT)
 from refpath import ref_render
-from views import make_view, config2, SEAHORSE, deep_embedded_julia, honeytrace
+from views import make_view, config2, config4m, SEAHORSE, deep_embedded_julia, honeytrace
 
 pytestmark = pytest.mark.gpu
 
@@ -138,6 +138,40 @@ def test_gmp_precisions_seahorse(ref_lib, prec):
 @pytest.mark.parametrize("prec", [128, 320])
 def test_gmp_fractals(ref_lib, fractal, prec):
     check_gmp(make_view("-0.5", "-0.3", "3.5", 96, 72, mode="gmp", precision=prec, depth=300, fractal=fractal), ref_lib)
+
+
+# Above 512 bits mpf values are held by a group of 16 or 32 lanes (coop_mpf.cuh): the four shapes at precisions
+# that fill them (P + 2 limbs of T K / 2) and that do not; the reference takes any precision (src/image_info.c:535).
+@pytest.mark.parametrize("prec", [513, 600, 1024, 1856, 1857, 2048, 3904, 4096, 5952, 6000, 8000])
+def test_gmp_wide_precisions_lane_groups(ref_lib, prec):
+    w, h = (64, 48) if prec <= 4096 else (40, 30)
+    v = make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", w, h, mode="gmp", precision=prec, depth=1500)
+    p = mdz_b200.Plan(v, 0)
+    ki = p.kernel_info()
+    p.close()
+    assert ki["lanes_per_pixel"] == (16 if prec <= 3904 else 32) and ki["limbs"] == 2 * ((prec + 127) // 64 + 1)
+    raw = check_gmp(v, ref_lib)
+    assert (raw > 0).any()
+
+
+@pytest.mark.parametrize("fractal", [MANDELBROT, BURNING_SHIP, GENERALIZED_CELTIC, VARIANT])
+def test_gmp_1024_fractals_julia_and_antialias(ref_lib, fractal):
+    check_gmp(make_view("-0.5", "-0.3", "3.5", 64, 48, mode="gmp", precision=1024, depth=300, fractal=fractal), ref_lib)
+    check_gmp(make_view("0", "0", "3.2", 48, 36, mode="gmp", precision=1024, depth=300, fractal=fractal, aa=2,
+                        family=FAMILY_JULIA, julia=("-0.8", "0.156")), ref_lib, threads=1)
+
+
+def test_gmp_1024_real_axis_and_minibrot(ref_lib):
+    check_gmp(make_view("-0.75", "0.0", "2.5", 48, 36, mode="gmp", precision=1024, depth=400), ref_lib)
+    raw = check_gmp(config4m(32, 18, 7000, mode="gmp", precision=1024), ref_lib)
+    assert (raw == 0).any() and (raw > 0).any()
+
+
+def test_gmp_beyond_the_kernels_is_refused():
+    v = make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", 16, 12, mode="gmp", precision=8001, depth=100)
+    assert not mdz_b200.view_supported(v)
+    with pytest.raises(mdz_b200.MdzCudaError):
+        mdz_b200.Plan(v, 0)
 
 
 def test_gmp_julia_one_digit_constant(ref_lib):
