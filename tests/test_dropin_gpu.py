@@ -78,6 +78,25 @@ def test_precision_2048_file_renders_on_the_gpu(tmp_path):
     assert np.array_equal(got_rgb, want_rgb)
 
 
+def test_gmp_precision_1024_file_renders_on_the_gpu(tmp_path):
+    """gallery/space_pad.mdz (GMP mpf mode) at `precision 1024`: above the one-thread mpf kernels, so the drop-in
+    renders it with the lane-group kernels (coop_mpf.cuh) -- same raw_data as the stock binary, no fallback line
+    (run_cmdline asserts that stderr does not mention libmdzcuda)."""
+    stock, ours = os.path.join(REF, "mdz"), os.path.join(REF, "mdz_cuda")
+    if not (os.path.exists(stock) and os.path.exists(ours)):
+        pytest.skip("oracle/_ref binaries not built")
+    meta, _, _ = G.load("space_pad_asis")
+    m = dict(meta)
+    text = meta["mdz_text"].replace("precision 128\n", "precision 1024\n")
+    assert text != meta["mdz_text"] and "multi-rounding no" in text
+    m.update(mdz_text=text, width=96, height=72, precision=1024, name="gmpwide1024")
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    want_raw, want_rgb = run_cmdline(stock, m, tmp_path / "a")
+    got_raw, got_rgb = run_cmdline(ours, m, tmp_path / "b")
+    assert np.array_equal(got_raw, want_raw), "%d raw pixels differ" % int((got_raw != want_raw).sum())
+    assert (got_raw > 0).any()
+
+
 def test_precision_beyond_the_kernels_falls_back_to_the_host_callback(tmp_path):
     """`precision 16384` is a legal setting (src/image_info.c:535: 80..99999999) with no GPU kernel: the drop-in must
     render it with MDZ's own line callback -- correct image, one line on stderr -- not report a blank one as done."""

@@ -39,14 +39,19 @@ for p in (128, 192, 256, 320, 384, 448, 512):
     st = spills.get(("g", ki["limbs"]), ("?", "?", "?"))
     print("| GMP mpf | %d | %d | %d | %s | %s / %s | %d | %d | %d |" % (p, ki["limbs"], ki["regs_per_thread"], st[0], st[1], st[2],
                                                                     ki["shared_bytes"], ki["blocks_per_sm"], ki["blocks_per_sm"] * 4))
-for p in (2048, 4096, 6144, 8192):
-    v = make_view("-0.5", "0", "3", 32, 24, mode="mpfr", precision=p, depth=10)
-    plan = mdz_b200.Plan(v, 0)
-    plan.launch(); plan.wait()
-    ki = plan.kernel_info()
-    plan.close()
-    kk, tt = {2048: (4, 16), 4096: (8, 16), 6144: (6, 32), 8192: (8, 32)}[p]
-    m = re.search(r"Compiling entry function '_ZN3mdz18escape_coop_kernelILi%dELi%dEE.*?\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads" % (kk, tt), rep)
-    st = m.groups() if m else ("?", "?", "?")
-    print("| MPFR, %d lanes per pixel |" % ki["lanes_per_pixel"] + " %d | %d | %d | %s | %s / %s | %d | %d | %d |" % (p, ki["limbs"], ki["regs_per_thread"], st[0], st[1], st[2],
-                                                                                     ki["shared_bytes"], ki["blocks_per_sm"], ki["blocks_per_sm"] * 4))
+for mode, precs in (("mpfr", (2048, 4096, 6144, 8192)), ("gmp", (1024, 1856, 3904, 5952, 8000))):
+    for p in precs:
+        v = make_view("-0.5", "0", "3", 32, 24, mode=mode, precision=p, depth=10)
+        plan = mdz_b200.Plan(v, 0)
+        plan.launch(); plan.wait()
+        ki = plan.kernel_info()
+        plan.close()
+        tt = ki["lanes_per_pixel"]
+        kk = {("mpfr", 2048): 4, ("mpfr", 4096): 8, ("mpfr", 6144): 6, ("mpfr", 8192): 8,
+              ("gmp", 1024): 4, ("gmp", 1856): 4, ("gmp", 3904): 8, ("gmp", 5952): 6, ("gmp", 8000): 8}[(mode, p)]
+        m = re.search(r"Compiling entry function '_ZN3mdz18escape_coop_kernelILi%dELi%dELb%dEE.*?\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads"
+                      % (kk, tt, 1 if mode == "gmp" else 0), rep)
+        st = m.groups() if m else ("?", "?", "?")
+        print("| %s, %d lanes x %d words per pixel |" % ("GMP mpf" if mode == "gmp" else "MPFR", tt, kk)
+              + " %d | %d | %d | %s | %s / %s | %d | %d | %d |" % (p, ki["limbs"], ki["regs_per_thread"], st[0], st[1], st[2],
+                                                                 ki["shared_bytes"], ki["blocks_per_sm"], ki["blocks_per_sm"] * 4))

@@ -9,6 +9,8 @@ run $S --tool racecheck python tools/run_case.py sea2048 --scale 0.03
 run $S --tool racecheck python tools/run_case.py sea4096 --scale 0.02
 run $S --tool synccheck python tools/run_case.py sea2048 --scale 0.03
 run $S --tool racecheck python tools/run_case.py sea8192 --scale 0.02
+run $S --tool racecheck python tools/run_case.py gmp1024 --scale 0.03
+run $S --tool memcheck python tools/run_case.py gmp2048 --scale 0.03
 run $S --tool memcheck python tools/run_case.py mini --scale 0.08 --order 1 --depth 3000
 run $S --tool racecheck python tools/run_case.py mini --scale 0.05 --order 1 --depth 3000
 run $S --tool memcheck python tools/run_case.py ld --scale 0.1 --order 1
