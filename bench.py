@@ -251,6 +251,7 @@ def side_precisions(torch, device, peak, peak32, skip=()):
         ("mpfr2048", sea(480, 270, precision=2048)),
         ("mpfr4096", sea(320, 180, precision=4096)),
         ("mpfr8192", sea(240, 135, precision=8192)),
+        ("gmp768", sea(960, 540, mode="gmp", precision=768)),
         ("gmp1024", sea(480, 270, mode="gmp", precision=1024)),
         ("gmp2048", sea(240, 135, mode="gmp", precision=2048)),
     ]

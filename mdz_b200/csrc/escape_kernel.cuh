@@ -673,7 +673,7 @@ escape_gmp_kernel(const EscapeParams p)
 template <int NW> struct GSmemWords { static constexpr int value = 2 * NW + GScratchWords<NW>::value; };
 // (measured on the B200: 14 words -- 320 bits -- 15.1 -> 16.4 G it/s with 4 blocks of 128 registers instead of 3 of 168;
 // 20 words -- 512 bits -- 8.9 -> 8.0, the spills outweigh the fourth block)
-template <int NW> struct GMinBlocks { static constexpr int value = NW <= 8 ? 6 : NW <= 14 ? 4 : 3; };
+template <int NW> struct GMinBlocks { static constexpr int value = NW <= 8 ? 6 : NW <= 14 ? 4 : NW <= 20 ? 3 : NW <= 24 ? 2 : 1; };
 
 template <int NW>
 __device__ __forceinline__ void load_gf_entry(const CoordTable& t, int i, GF<NW>& v)

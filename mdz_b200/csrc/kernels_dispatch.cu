@@ -36,13 +36,19 @@ int mdz_smem_words_mpfr(int n)
 
 kernel_fn kernels_gmpf_a_kernel(int nl); int kernels_gmpf_a_smem(int nl);
 kernel_fn kernels_gmpf_b_kernel(int nl); int kernels_gmpf_b_smem(int nl);
+kernel_fn kernels_gmpf_c_kernel(int nl); int kernels_gmpf_c_smem(int nl);
+kernel_fn kernels_gmpf_d_kernel(int nl); int kernels_gmpf_d_smem(int nl);
 kernel_fn mdz_kernel_gmp_fast(int nl)
 {
     kernel_fn f = kernels_gmpf_a_kernel(nl);
-    return f ? f : kernels_gmpf_b_kernel(nl);
+    if (!f) f = kernels_gmpf_b_kernel(nl);
+    if (!f) f = kernels_gmpf_c_kernel(nl);
+    return f ? f : kernels_gmpf_d_kernel(nl);
 }
 int mdz_smem_words_gmp_fast(int nl)
 {
     int w = kernels_gmpf_a_smem(nl);
-    return w ? w : kernels_gmpf_b_smem(nl);
+    if (!w) w = kernels_gmpf_b_smem(nl);
+    if (!w) w = kernels_gmpf_c_smem(nl);
+    return w ? w : kernels_gmpf_d_smem(nl);
 }

@@ -173,7 +173,7 @@ def test_ops_match_libgmp(emu, p):
         assert emu_op(emu, 4, c, c) == (1 if mpf_cmp(c.ref, four.ref) > 0 else 0)
 
 
-@pytest.mark.parametrize("p", [80, 128, 200, 256, 320, 512, 1024])
+@pytest.mark.parametrize("p", [80, 128, 200, 256, 320, 512, 576, 640, 704, 768, 832, 896, 1024])
 def test_fast_ops_match_libgmp(emu, p):
     """mpf_fast.cuh (the register / IMAD.WIDE implementation the kernel uses)."""
     P = prec_limbs(p)
@@ -193,7 +193,7 @@ def test_fast_ops_match_libgmp(emu, p):
         assert emu_op(emu, 4, c, c, True) == (1 if mpf_cmp(c.ref, four.ref) > 0 else 0)
 
 
-@pytest.mark.parametrize("p", [80, 128, 320, 512])
+@pytest.mark.parametrize("p", [80, 128, 320, 512, 640, 896])
 def test_fast_products_next_to_truncation_boundary(emu, p):
     """gf_mul forms only the high columns of the product and falls back to the full
     product when the guard word is within the truncation error of wrapping.  Build

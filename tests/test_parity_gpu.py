@@ -140,16 +140,17 @@ def test_gmp_fractals(ref_lib, fractal, prec):
     check_gmp(make_view("-0.5", "-0.3", "3.5", 96, 72, mode="gmp", precision=prec, depth=300, fractal=fractal), ref_lib)
 
 
-# Above 512 bits mpf values are held by a group of 16 or 32 lanes (coop_mpf.cuh): the four shapes at precisions
-# that fill them (P + 2 limbs of T K / 2) and that do not; the reference takes any precision (src/image_info.c:535).
-@pytest.mark.parametrize("prec", [513, 600, 1024, 1856, 1857, 2048, 3904, 4096, 5952, 6000, 8000])
+# One thread per pixel to 16 limbs (896 bits; mpf_fast.cuh), above that mpf values are held by a group of 16 or 32
+# lanes (coop_mpf.cuh): the four shapes at precisions that fill them (P + 2 limbs of T K / 2) and that do not; the
+# reference takes any precision (src/image_info.c:535).
+@pytest.mark.parametrize("prec", [513, 600, 704, 768, 832, 896, 897, 1024, 1856, 1857, 2048, 3904, 4096, 5952, 6000, 8000])
 def test_gmp_wide_precisions_lane_groups(ref_lib, prec):
     w, h = (64, 48) if prec <= 4096 else (40, 30)
     v = make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", w, h, mode="gmp", precision=prec, depth=1500)
     p = mdz_b200.Plan(v, 0)
     ki = p.kernel_info()
     p.close()
-    assert ki["lanes_per_pixel"] == (16 if prec <= 3904 else 32) and ki["limbs"] == 2 * ((prec + 127) // 64 + 1)
+    assert ki["lanes_per_pixel"] == (1 if prec <= 896 else 16 if prec <= 3904 else 32) and ki["limbs"] == 2 * ((prec + 127) // 64 + 1)
     raw = check_gmp(v, ref_lib)
     assert (raw > 0).any()
 

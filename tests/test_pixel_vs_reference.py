@@ -166,6 +166,8 @@ GCASES = [
     ("celtic gmp 320", lambda: make_view("-0.5", "-0.3", "3.5", 96, 72, mode="gmp", precision=320, depth=300, fractal=GENERALIZED_CELTIC), 100),
     ("hybrid gmp 128", lambda: make_view("-0.5", "-0.3", "3.5", 96, 72, mode="gmp", precision=128, depth=300, fractal=VARIANT), 100),
     ("real axis gmp 128", lambda: make_view("-0.75", "0.0", "2.5", 64, 48, mode="gmp", precision=128, depth=500), 64),
+    ("seahorse gmp 896", lambda: make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", 96, 72, mode="gmp", precision=896, depth=1500), 8),
+    ("celtic gmp 640", lambda: make_view("-0.5", "-0.3", "3.5", 96, 72, mode="gmp", precision=640, depth=300, fractal=GENERALIZED_CELTIC), 40),
 ]
 
 

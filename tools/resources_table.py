@@ -30,7 +30,7 @@ for label, mode, p in rows:
     st = spills.get((ki["limbs"], 0), ("?", "?", "?"))
     print("| %s | %d | %d | %d | %s | %s / %s | %d | %d | %d |" % (label, p, ki["limbs"], ki["regs_per_thread"], st[0], st[1], st[2],
                                                               ki["shared_bytes"], ki["blocks_per_sm"], ki["blocks_per_sm"] * 4))
-for p in (128, 192, 256, 320, 384, 448, 512):
+for p in (128, 192, 256, 320, 384, 448, 512, 576, 640, 704, 768, 832, 896):
     v = make_view("-0.5", "0", "3", 32, 24, mode="gmp", precision=p, depth=10)
     plan = mdz_b200.Plan(v, 0)
     plan.launch(); plan.wait()
