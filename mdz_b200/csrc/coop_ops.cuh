@@ -1,8 +1,8 @@
 // coop_ops.cuh -- MPFR-faithful soft floating point with a GROUP OF LANES PER VALUE: the significand's
-// N = T K limbs are split over T lanes (T = 32: a warp per value; T = 16: two values per warp), K
+// N = T K limbs are split over T lanes (T = 32: a warp per value; T = 16, 8: two, four values per warp), K
 // consecutive limbs each (lane 0 of the group the least significant), sign and exponent are
 // group-uniform scalars.  For precisions beyond what one thread can hold in registers (above 1024
-// bits: T x K = 16 x 4, 16 x 8, 32 x 6, 32 x 8 -> 2048, 4096, 6144, 8192 bits).
+// bits: T x K = 8 x 8, 16 x 8, 32 x 6, 32 x 8 -> 2048, 4096, 6144, 8192 bits).
 //
 // Same contract as mpfr_sf.cuh -- "exact result, rounded once to p bits, nearest, ties to even",
 // i.e. mpfr_mul / mpfr_add / mpfr_sub with MPFR_RNDN as the reference's loops call them

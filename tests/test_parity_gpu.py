@@ -38,7 +38,7 @@ def test_mpfr_precisions_seahorse(ref_lib, prec):
     check(make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", 96, 72, precision=prec, depth=1500), ref_lib)
 
 
-# Above 1024 bits a pixel is rendered by a group of 16 or 32 lanes (coop_kernel.cuh: limbs split over the lanes,
+# Above 1024 bits a pixel is rendered by a group of 8, 16 or 32 lanes (coop_kernel.cuh: limbs split over the lanes,
 # shuffle products, ballot carries).  The reference accepts any precision from 80 bits up (src/image_info.c:535);
 # kernels are instantiated to 8192 bits.  Precisions that fill the lanes' 1024 K bits and that do not.
 @pytest.mark.parametrize("prec", [1025, 1100, 2048, 3000, 4096, 6144, 8192])
@@ -46,7 +46,7 @@ def test_mpfr_wide_precisions_warp_per_pixel(ref_lib, prec):
     w, h = (64, 48) if prec <= 4096 else (40, 30)
     v = make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", w, h, precision=prec, depth=1500)
     p = mdz_b200.Plan(v, 0)
-    assert p.kernel_info()["lanes_per_pixel"] == (16 if prec <= 4096 else 32) and p.kernel_info()["limbs"] == (prec + 31) // 32
+    assert p.kernel_info()["lanes_per_pixel"] == (8 if prec <= 2048 else 16 if prec <= 4096 else 32) and p.kernel_info()["limbs"] == (prec + 31) // 32
     p.close()
     raw = check(v, ref_lib)
     assert (raw > 0).any()
@@ -150,7 +150,7 @@ def test_gmp_wide_precisions_lane_groups(ref_lib, prec):
     p = mdz_b200.Plan(v, 0)
     ki = p.kernel_info()
     p.close()
-    assert ki["lanes_per_pixel"] == (1 if prec <= 896 else 16 if prec <= 3904 else 32) and ki["limbs"] == 2 * ((prec + 127) // 64 + 1)
+    assert ki["lanes_per_pixel"] == (1 if prec <= 896 else 8 if prec <= 1856 else 16 if prec <= 3904 else 32) and ki["limbs"] == 2 * ((prec + 127) // 64 + 1)
     raw = check_gmp(v, ref_lib)
     assert (raw > 0).any()
 
