@@ -1,6 +1,6 @@
 // coop_kernel.cuh -- the escape-time loop with A GROUP OF LANES PER PIXEL, for MPFR precisions above 1024 bits
 // (33 to 256 limbs: more than a thread can keep in registers).  T lanes hold a pixel's values, K limbs each
-// (coop_ops.cuh): 8 x 8 and 16 x 8 -- four and two pixels per warp -- for up to 2048 and 4096 bits, 32 x 6 and 32 x 8 for
+// (coop_ops.cuh): 8 x 6, 8 x 8 and 16 x 8 -- four, four and two pixels per warp -- for up to 1536, 2048 and 4096 bits, 32 x 6 and 32 x 8 for
 // 6144 and 8192.  Same pixel queue, band completion, cancel word and fed-plan protocol as the one-thread-per-pixel
 // kernels (escape_kernel.cuh); a group claims one pixel at a time.  Restates the reference's frac_*_mpfr loops
 // (src/frac_mandel.c:25-52, src/frac_burning_ship.c:27-55, src/frac_generalized_celtic.c:27-55,

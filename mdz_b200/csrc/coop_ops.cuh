@@ -2,7 +2,7 @@
 // N = T K limbs are split over T lanes (T = 32: a warp per value; T = 16, 8: two, four values per warp), K
 // consecutive limbs each (lane 0 of the group the least significant), sign and exponent are
 // group-uniform scalars.  For precisions beyond what one thread can hold in registers (above 1024
-// bits: T x K = 8 x 8, 16 x 8, 32 x 6, 32 x 8 -> 2048, 4096, 6144, 8192 bits).
+// bits: T x K = 8 x 6, 8 x 8, 16 x 8, 32 x 6, 32 x 8 -> 1536, 2048, 4096, 6144, 8192 bits).
 //
 // Same contract as mpfr_sf.cuh -- "exact result, rounded once to p bits, nearest, ties to even",
 // i.e. mpfr_mul / mpfr_add / mpfr_sub with MPFR_RNDN as the reference's loops call them

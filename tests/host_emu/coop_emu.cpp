@@ -79,6 +79,7 @@ extern "C" int coop_binop(int K, int T, int op, long prec, const uint64_t* al, i
     case 816: return binop<8, 16>(op, prec, al, as, ae, bl, bs, be, rl, rs, re);
     case 216: return binop<2, 16>(op, prec, al, as, ae, bl, bs, be, rl, rs, re);
     case 808: return binop<8, 8>(op, prec, al, as, ae, bl, bs, be, rl, rs, re);
+    case 608: return binop<6, 8>(op, prec, al, as, ae, bl, bs, be, rl, rs, re);
     default: return 0;
     }
 }
@@ -116,6 +117,7 @@ extern "C" long coop_pixel(int K, int T, long prec, int fractal, long depth,
     case 816: return pixel<8, 16>(prec, fractal, depth, l, sg, ex);
     case 216: return pixel<2, 16>(prec, fractal, depth, l, sg, ex);
     case 808: return pixel<8, 8>(prec, fractal, depth, l, sg, ex);
+    case 608: return pixel<6, 8>(prec, fractal, depth, l, sg, ex);
     default: return -1;
     }
 }

@@ -79,6 +79,7 @@ static int gop(int op, int nl, const uint64_t* al, long ae, int as, const uint64
     case 832: return F<8, 32>(__VA_ARGS__); \
     case 432: return F<4, 32>(__VA_ARGS__); \
     case 808: return F<8, 8>(__VA_ARGS__); \
+    case 608: return F<6, 8>(__VA_ARGS__); \
     default: return 0; \
     }
 

@@ -19,9 +19,9 @@ from views import make_view, SEAHORSE
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # (K words per lane, T lanes per value, mpf precision in bits): a value of P + 1 limbs needs (P + 2) limbs of T K / 2.
-# 8 x 8 (to 1856 bits), 16 x 8 (3904), 32 x 6 (5952), 32 x 8 (8000) are what the kernels use
+# 8 x 6 (to 1344 bits), 8 x 8 (1856), 16 x 8 (3904), 32 x 6 (5952), 32 x 8 (8000) are what the kernels use
 CASES = [(4, 16, 576), (4, 16, 1024), (4, 16, 1856), (8, 16, 1857), (8, 16, 2048), (8, 16, 3904),
-         (6, 32, 4096), (6, 32, 5952), (8, 32, 6000), (8, 32, 8000), (4, 32, 2048), (4, 16, 128), (8, 8, 1856), (8, 8, 897)]
+         (6, 32, 4096), (6, 32, 5952), (8, 32, 6000), (8, 32, 8000), (4, 32, 2048), (4, 16, 128), (8, 8, 1856), (8, 8, 1345), (6, 8, 1344), (6, 8, 897), (6, 8, 1024)]
 
 
 @pytest.fixture(scope="module")

@@ -19,9 +19,9 @@ from views import make_view, SEAHORSE, MINIBROT120
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # (K limbs per lane, T lanes per value: T K limbs = 32 T K bits of working width), precisions that fill it and that do not;
-# 8 x 8, 16 x 8, 32 x 6, 32 x 8 are what the kernels use, the others exercise the same code at other shapes
+# 8 x 6, 8 x 8, 16 x 8, 32 x 6, 32 x 8 are what the kernels use, the others exercise the same code at other shapes
 CASES = [(4, 16, 2048), (4, 16, 1025), (4, 16, 1100), (4, 16, 2047), (4, 16, 1984), (8, 16, 4096), (8, 16, 2049), (8, 16, 3000),
-         (6, 32, 6144), (6, 32, 5000), (8, 32, 8192), (8, 32, 7000), (2, 32, 2048), (4, 32, 4096), (2, 16, 1024), (2, 16, 700), (8, 8, 2048), (8, 8, 1025)]
+         (6, 32, 6144), (6, 32, 5000), (8, 32, 8192), (8, 32, 7000), (2, 32, 2048), (4, 32, 4096), (2, 16, 1024), (2, 16, 700), (8, 8, 2048), (8, 8, 1537), (6, 8, 1536), (6, 8, 1025), (6, 8, 1100)]
 
 
 @pytest.fixture(scope="module")

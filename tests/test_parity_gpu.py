@@ -41,7 +41,7 @@ def test_mpfr_precisions_seahorse(ref_lib, prec):
 # Above 1024 bits a pixel is rendered by a group of 8, 16 or 32 lanes (coop_kernel.cuh: limbs split over the lanes,
 # shuffle products, ballot carries).  The reference accepts any precision from 80 bits up (src/image_info.c:535);
 # kernels are instantiated to 8192 bits.  Precisions that fill the lanes' 1024 K bits and that do not.
-@pytest.mark.parametrize("prec", [1025, 1100, 2048, 3000, 4096, 6144, 8192])
+@pytest.mark.parametrize("prec", [1025, 1100, 1536, 1537, 2048, 3000, 4096, 6144, 8192])
 def test_mpfr_wide_precisions_warp_per_pixel(ref_lib, prec):
     w, h = (64, 48) if prec <= 4096 else (40, 30)
     v = make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", w, h, precision=prec, depth=1500)
@@ -143,7 +143,7 @@ def test_gmp_fractals(ref_lib, fractal, prec):
 # One thread per pixel to 16 limbs (896 bits; mpf_fast.cuh), above that mpf values are held by a group of 16 or 32
 # lanes (coop_mpf.cuh): the four shapes at precisions that fill them (P + 2 limbs of T K / 2) and that do not; the
 # reference takes any precision (src/image_info.c:535).
-@pytest.mark.parametrize("prec", [513, 600, 704, 768, 832, 896, 897, 1024, 1856, 1857, 2048, 3904, 4096, 5952, 6000, 8000])
+@pytest.mark.parametrize("prec", [513, 600, 704, 768, 832, 896, 897, 1024, 1344, 1345, 1856, 1857, 2048, 3904, 4096, 5952, 6000, 8000])
 def test_gmp_wide_precisions_lane_groups(ref_lib, prec):
     w, h = (64, 48) if prec <= 4096 else (40, 30)
     v = make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", w, h, mode="gmp", precision=prec, depth=1500)

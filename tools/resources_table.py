@@ -47,8 +47,7 @@ for mode, precs in (("mpfr", (2048, 4096, 6144, 8192)), ("gmp", (1024, 1856, 390
         ki = plan.kernel_info()
         plan.close()
         tt = ki["lanes_per_pixel"]
-        kk = {("mpfr", 2048): 4, ("mpfr", 4096): 8, ("mpfr", 6144): 6, ("mpfr", 8192): 8,
-              ("gmp", 1024): 4, ("gmp", 1856): 4, ("gmp", 3904): 8, ("gmp", 5952): 6, ("gmp", 8000): 8}[(mode, p)]
+        kk = 6 if p in (6144, 5952) else 8
         m = re.search(r"Compiling entry function '_ZN3mdz18escape_coop_kernelILi%dELi%dELb%dEE.*?\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads"
                       % (kk, tt, 1 if mode == "gmp" else 0), rep)
         st = m.groups() if m else ("?", "?", "?")
