@@ -110,7 +110,12 @@ escape_coop_kernel(const EscapeParams p)
             }
             __syncwarp();
             if (publish_bands(p, finished_band, lane)) finished_band = -1;
-            if (__any_sync(0xffffffffu, !active)) break;        // a group is free: refill before going on
+            if (__any_sync(0xffffffffu, !active)) {
+                // a group is free: refill before going on -- unless the queue has nothing left to give, in which case
+                // the groups still at work keep the chunk (no poll of the cancel word per iteration in the tail)
+                if (!__any_sync(0xffffffffu, active)) break;
+                if (!exhausted || (p.feed && __any_sync(0xffffffffu, !active && (pix & kReserved) != 0u))) break;
+            }
         }
     }
 }
