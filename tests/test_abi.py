@@ -60,3 +60,21 @@ def test_null_plan_is_an_error_not_a_crash():
     assert lib.mdzcuda_plan_kernels_launched(None) == -1
     assert lib.mdzcuda_plan_set_parking(None, 1) == 0
     assert b"null plan" in lib.mdzcuda_last_error()
+
+
+def test_view_supported_states_the_precision_limits():
+    """mdzcuda_view_supported answers without a device: MDZ admits 80..99999999 bits (src/image_info.c:535), kernels
+    exist for MPFR 33..8192 bits and GMP mpf to 8000 bits; everything else goes to the host's line callback behind
+    rth_*  and is refused by the plain entry points with a reason."""
+    import mdz_b200
+    from views import make_view, SEAHORSE
+    def ok(mode, prec):
+        return mdz_b200.view_supported(make_view(SEAHORSE[0], SEAHORSE[1], "1e-9", 16, 12, mode=mode, precision=prec, depth=10))
+    for prec in (80, 1024, 1025, 1536, 1537, 2048, 2049, 4096, 4097, 6144, 6145, 8192):
+        assert ok("mpfr", prec), prec
+    assert not ok("mpfr", 8193) and "8192" in mdz_b200.last_error()
+    assert not ok("mpfr", 99999999)
+    for prec in (80, 512, 513, 896, 897, 1344, 1345, 1856, 1857, 3904, 3905, 5952, 5953, 8000):
+        assert ok("gmp", prec), prec
+    assert not ok("gmp", 8001) and "8000" in mdz_b200.last_error()
+    assert ok("ld", 80)
