@@ -90,7 +90,7 @@ int mdzcuda_device_count(void);
 /*
  * 1 when a GPU kernel is instantiated for the view's mode and precision, else 0 with the reason in
  * mdzcuda_last_error().  MDZ's settings admit 80..99999999 bits (src/image_info.c:535); kernels exist
- * for long double, MPFR 33..8192 bits (one thread per pixel to 1024 bits, 16 or 32 lanes per pixel above) and GMP mpf to 8000 bits (one thread to 896, lane groups above).  The rth_* layer renders everything else
+ * for long double, MPFR 33..8192 bits (one thread per pixel to 1024 bits, 8, 16 or 32 lanes per pixel above) and GMP mpf to 8000 bits (one thread to 896, lane groups above).  The rth_* layer renders everything else
  * with the line callback the host installed (src/image_info.c:243-248), i.e. on the CPU, with one line
  * on stderr -- see mdzcuda_fallback_lines.
  */
@@ -242,7 +242,7 @@ typedef struct mdzcuda_kernel_info {
     int blocks_per_sm;
     int grid_blocks;
     int sm_count;
-    int lanes_per_pixel;    /* 1: one thread per pixel; 16 / 32: a group of lanes per pixel (MPFR above 1024 bits, GMP above 896) */
+    int lanes_per_pixel;    /* 1: one thread per pixel; 8 / 16 / 32: a group of lanes per pixel (MPFR above 1024 bits, GMP above 896) */
 } mdzcuda_kernel_info;
 int mdzcuda_plan_kernel_info(mdzcuda_plan*, mdzcuda_kernel_info* out);
 
