@@ -15,7 +15,7 @@ from mdz_b200 import MANDELBROT, BURNING_SHIP, GENERALIZED_CELTIC, VARIANT
 from mdz_b200.mp import mpf_mul, mpf_mul_ui, mpf_add, mpf_sub, mpf_cmp
 from test_arith_vs_gmp import G, U64, canon, prec_limbs, rand_pair
 from test_pixel_vs_reference import gmp_coords, gmp_ref_pixel, fixed_mpf
-from views import make_view, SEAHORSE
+from views import make_view, SEAHORSE, gmp_close_path_view
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # (K words per lane, T lanes per value, mpf precision in bits): a value of P + 1 limbs needs (P + 2) limbs of T K / 2.
@@ -106,3 +106,39 @@ def test_pixels_match_reference(coop, ref_lib, name, K, T, mk, count):
         assert got == gmp_ref_pixel(ref_lib, view, x, y), (name, ix, line)
         seen.add(got)
     assert len(seen) > 2, "every sampled pixel gave the same count"
+
+
+@pytest.mark.parametrize("K,T,prec", [(6, 8, 1024), (8, 8, 1800), (8, 16, 2048), (6, 32, 4096)])
+def test_close_subtraction_inside_a_pixel(coop, ref_lib, K, T, prec):
+    """tests/views.py gmp_close_path_view: every pixel's first wre2 - wim2 takes the one-limb-gap path (counted), and
+    the pixel still comes out as the reference's frac_mandel_gmp computes it."""
+    view = gmp_close_path_view(prec, 8, 6)
+    nl = (max(53, prec) + 127) // 64 + 1
+    from mdz_b200.mp import Mpf, mpf_set_str
+    cx, cy = Mpf(prec, "-1"), Mpf(prec, "0.3")
+    for ix, line in ((0, 0), (3, 0), (0, 4), (7, 5)):
+        x, y = gmp_coords(view, ix, line)
+        before = coop.coop_gmp_close_calls()
+        args = []
+        for v in (x, y, cx, cy):
+            args += list(fixed_mpf(v, nl))
+        got = coop.coop_gmp_pixel(K, T, nl, view.fractal, view.depth, *args)
+        assert coop.coop_gmp_close_calls() > before, "the pixel did not reach the close subtraction"
+        assert got == gmp_ref_pixel_julia(ref_lib, view, x, y, cx, cy) and got > 0
+
+
+def gmp_ref_pixel_julia(ref, view, x, y, cx, cy):
+    """frac_*_gmp on z0 = (x, y) with the constant (cx, cy): fractal.c:331-342's set-up"""
+    from test_pixel_vs_reference import GFRAC, GP
+    from mdz_b200.mp import Mpf, mpf_set, mpf_set_si, mpf_mul
+    p = view.precision
+    fn = getattr(ref, GFRAC[view.fractal])
+    fn.restype = C.c_long
+    fn.argtypes = [C.c_long] + [GP] * 8
+    bail, wim, wre, cim, cre, wim2, wre2, t1 = (Mpf(p) for _ in range(8))
+    mpf_set_si(bail.ref, 4)
+    for dst, src in ((wim, y), (wre, x), (cim, cy), (cre, cx)):
+        mpf_set(dst.ref, src.ref)
+    mpf_mul(wim2.ref, y.ref, y.ref)
+    mpf_mul(wre2.ref, x.ref, x.ref)
+    return fn(view.depth, bail.ptr, wim.ptr, wre.ptr, cim.ptr, cre.ptr, wim2.ptr, wre2.ptr, t1.ptr)

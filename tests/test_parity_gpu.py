@@ -9,7 +9,7 @@ import pytest
 import mdz_b200
 from mdz_b200 import (FAMILY_JULIA, MANDELBROT, BURNING_SHIP, GENERALIZED_CELTIC, VARIANT)
 from refpath import ref_render
-from views import make_view, config2, config4m, SEAHORSE, deep_embedded_julia, honeytrace
+from views import make_view, config2, config4m, SEAHORSE, deep_embedded_julia, honeytrace, gmp_close_path_view
 
 pytestmark = pytest.mark.gpu
 
@@ -166,6 +166,17 @@ def test_gmp_1024_real_axis_and_minibrot(ref_lib):
     check_gmp(make_view("-0.75", "0.0", "2.5", 48, 36, mode="gmp", precision=1024, depth=400), ref_lib)
     raw = check_gmp(config4m(32, 18, 7000, mode="gmp", precision=1024), ref_lib)
     assert (raw == 0).any() and (raw > 0).any()
+
+
+@pytest.mark.parametrize("prec", [128, 1024, 1800, 2048, 4096])
+def test_gmp_close_subtraction_in_every_pixel(ref_lib, prec):
+    """tests/views.py gmp_close_path_view: the first wre2 - wim2 of every pixel is GMP's one-limb-gap subtraction,
+    which the lane-group kernels hand to one lane over the shared-memory strip (coop_mpf.cuh cg_sub_close) and the
+    one-thread kernels to an out-of-line function -- paths no ordinary view reaches.  More pixels than groups, so
+    every strip is used again after it.  (tests/test_coop_vs_gmp.py checks on the CPU that these pixels do take it.)"""
+    w, h = (128, 96) if prec <= 2048 else (64, 48)
+    raw = check_gmp(gmp_close_path_view(prec, w, h, depth=200), ref_lib, threads=1)
+    assert (raw > 0).all()
 
 
 def test_gmp_beyond_the_kernels_is_refused():

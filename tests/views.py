@@ -99,3 +99,21 @@ def config4m(w=3840, h=2160, depth=100000, mode="mpfr", precision=512):
 def config5(fractal, w=7680, h=4320, aa=3, depth=1000, mode="ld", precision=64):
     cy = "-0.5" if fractal == BURNING_SHIP else "0.0"
     return make_view("-0.5", cy, "4.0", w, h, mode=mode, precision=precision, depth=depth, aa=aa, fractal=fractal)
+
+
+def gmp_close_path_view(precision, w=8, h=6, depth=3000, julia=("-1", "0.3")):
+    """A GMP-mode Julia view 1e-130 wide whose top left pixel is x = 2^-32, y = 2^-32 - 2^-98 exactly (ix = 0 and
+    line 0 reproduce gxmin and gymax bit for bit, src/fractal.c:310-328) and whose other pixels differ from it only
+    some 370 bits further down.  For every pixel x^2 = 1:0:0:... (a one, then zero limbs) and y^2 = ff..ff:7f..f:...
+    one limb below it, so the first wre2 - wim2 of EVERY pixel is GMP's one-limb-gap "close" subtraction (SURVEY
+    Appendix E) -- an operand pattern ordinary views never produce -- with different low limbs each time."""
+    from mdz_b200 import FAMILY_JULIA
+    v = make_view("0", "0", "1e-130", w, h, mode="gmp", precision=precision, depth=depth, family=FAMILY_JULIA, julia=julia)
+    def put(m, limbs, exp):
+        for i, l in enumerate(limbs):
+            m.s.d[i] = l
+        m.s.size = len(limbs)
+        m.s.exp = exp
+    put(v.gxmin, [1 << 32], 0)
+    put(v.gymax, [(1 << 64) - (1 << 30), (1 << 32) - 1], 0)
+    return v
