@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include "image_info.h"
 #include "fractal.h"
 #include "render_threads.h"
@@ -26,6 +27,22 @@ static void cp_mpfr(mpfr_t dst, const __mpfr_struct* src, mpfr_prec_t prec)
 {
     mpfr_init2(dst, prec);
     if (src) mpfr_set(dst, src, GMP_RNDN); else mpfr_set_si(dst, 0, GMP_RNDN);
+}
+
+#include <pthread.h>
+
+static void* ref_shutdown(void* p)
+{
+    image_info* img = p;
+    rth_ui_quit((rthdata*)img->rth_ptr);
+    free(img->raw_data);
+    mpfr_clear(img->xmin); mpfr_clear(img->xmax); mpfr_clear(img->ymax);
+    mpfr_clear(img->width);
+    mpfr_clear(img->u.julia.c_re); mpfr_clear(img->u.julia.c_im);
+    mpf_clear(img->gxmin); mpf_clear(img->gxmax); mpf_clear(img->gymax);
+    mpf_clear(img->gwidth);
+    free(img);
+    return 0;
 }
 
 int ref_render(int mode, long prec, int family, int fractal, long depth,
@@ -78,10 +95,13 @@ int ref_render(int mode, long prec, int family, int fractal, long depth,
                                         : fractal_gmp_calculate_line);
     rth_ui_init(rth);
     rth_ui_start_render(rth);
-    /* consumer loop shaped like render.c:49-92, without the colouring */
+    /* consumer loop shaped like render.c:49-92, without the colouring -- and without its
+     * rth_ui_wait_for_line_done(): that wait has no timeout (render_threads.c:568) and now and then misses the
+     * last signal (the reference's BUGS:1-6), which holds a test run for ever.  rth_process_lines_rendered()
+     * waits half a millisecond by itself; the pool that renders is untouched. */
     int y = 0, linesdone;
     do {
-        rth_ui_wait_for_line_done(rth);
+        usleep(100);
         linesdone = rth_process_lines_rendered(rth);
         if (linesdone) {
             int undrawn = 0;
@@ -98,16 +118,18 @@ int ref_render(int mode, long prec, int family, int fractal, long depth,
     } while (y < img->user_height);
     double t = rth_ui_get_render_time(rth);
     if (seconds) *seconds = t;
-    rth_ui_quit(rth);
-
     memcpy(raw_out, img->raw_data, npx * sizeof(int));
-    free(img->raw_data);
-    mpfr_clear(img->xmin); mpfr_clear(img->xmax); mpfr_clear(img->ymax);
-    mpfr_clear(img->width);
-    mpfr_clear(img->u.julia.c_re); mpfr_clear(img->u.julia.c_im);
-    mpf_clear(img->gxmin); mpf_clear(img->gxmax); mpf_clear(img->gymax);
-    mpf_clear(img->gwidth);
-    free(img);
+
+    /* rth_ui_quit() signals the watch thread's condition without setting the flag it waits on
+     * (render_threads.c:445-462 against :199-203): when the watch thread is not yet back in its wait -- a render
+     * of a few milliseconds -- the signal is lost and the join in rth_ui_quit never returns.  So the shutdown
+     * runs on a detached thread: in that rare case it leaks two sleeping threads instead of holding the caller. */
+    pthread_t th;
+    pthread_attr_t at;
+    pthread_attr_init(&at);
+    pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
+    if (pthread_create(&th, &at, ref_shutdown, img) != 0) ref_shutdown(img);
+    pthread_attr_destroy(&at);
     return 1;
 }
 
