@@ -125,12 +125,12 @@ def coop_pixel(lib, KT, view, x, y):
     return lib.coop_pixel(K, T, view.precision, view.fractal, view.depth, *args)
 
 
-@pytest.mark.parametrize("K,prec", [((4, 16), 2048), ((4, 16), 1100), ((8, 16), 4096), ((6, 32), 6144)])
+@pytest.mark.parametrize("K,prec", [((8, 8), 2048), ((6, 8), 1100), ((6, 8), 1536), ((4, 16), 2048), ((8, 16), 4096), ((6, 32), 6144)])
 @pytest.mark.parametrize("fractal", [MANDELBROT, BURNING_SHIP, GENERALIZED_CELTIC, VARIANT])
 def test_pixels_match_reference(coop, ref_lib, K, prec, fractal):
     views = [make_view(SEAHORSE[0], SEAHORSE[1], "1e-12", 64, 36, precision=prec, depth=400 if prec <= 2048 else 150, fractal=fractal),
              make_view("-0.5", "0.0", "4.0", 64, 36, precision=prec, depth=120, fractal=fractal)]
-    if fractal == MANDELBROT and prec == 2048:
+    if fractal == MANDELBROT and prec in (2048, 1536):
         # next to the period-707 minibrot: the orbit returns to ~0 (200 cancelled bits, then 400-bit gaps)
         views.append(make_view(MINIBROT120[0], MINIBROT120[1], "1e-120", 64, 36, precision=prec, depth=1500))
     for view in views:
